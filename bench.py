@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py -- trajectory-steps/sec of the FTL/FTRL regret sweep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: `--trials` seeded sequences per GPU
+(g-path family, keyed (base_seed, T, run) exactly like fast_algorithms.py:231-239) x T rounds
+x A (algorithm, eta0) variants, generated + simulated + compared by the fused sweep kernel,
+plus (N > 1) the NCCL all-reduce of the per-variant regret statistics.
+
+  workload c3 (default, BASELINE config 3): d = 1, T = 1e4, FTL + FTRL at 8 eta0 scales (A = 9)
+  workload c5 (BASELINE config 5 shape):     d = 5, T = 1e4, FTRL eta0 = sqrt 2 (A = 1), g(T) maximum
+
+value  : device-timed (CUDA events on the launching stream), seeds already on the device.
+e2e    : the same sweep through the public host API (engine.regret_sweep: host arguments in,
+         per-trajectory regrets + statistics copied back to host memory inside the timed region).
+         The reference API for this path (empirical_worst_case_thresholds(T_grid, runs, base_seed))
+         takes seeds, not arrays, so the per-step host->device payload is the variant table only.
+roofline: the sweep kernel generates its inputs on-chip, so its bound is the fp64 pipe, not HBM
+         (SURVEY.md 8d): achieved = (9d+6) algorithmic non-fused fp64 ops per trajectory-step x
+         trajectory-steps/s of the kernel; peak = non-FMA fp64 issue rate measured live by the
+         library's microbenchmark (MEASURED_PEAKS.json has no fp64 entry).
+cpu_baseline / --impl reference: the CPU oracle port of the same sweep (oracle/oco_oracle.c,
+         generation + A simulations per sequence, OpenMP over all host threads) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R2 = math.sqrt(2.0)
+WORKLOADS = {
+    "c3": dict(d=1, T=10_000, alg=[1] + [0] * 8, eta=[R2] + [R2 * s for s in (0.125, 0.25, 0.5, 1, 2, 4, 8, 16)],
+               trials=1_000_000, name="C3 batched d=1 regret sweep: T=1e4 x (FTL + FTRL x 8 eta0 scales)"),
+    "c5": dict(d=5, T=10_000, alg=[0], eta=[R2], trials=1_000_000,
+               name="C5 empirical g_T sweep: d=5, T=1e4, FTRL eta0=sqrt2"),
+}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set(); self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_sweep_rate(wl, budget_s: float, nthreads: int = 0):
+    """Oracle port timed on the host cores: returns (traj_steps_per_s, cores, sample description)."""
+    from oracle import oracle as O
+    A = len(wl["alg"])
+    cores = nthreads or O.num_threads()
+    n0 = max(cores, 8)
+    t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
+    dt0 = time.perf_counter() - t0
+    n = int(max(n0, min(200_000, n0 * budget_s / max(dt0, 1e-6))))
+    n -= n % cores or 0
+    n = max(n, cores)
+    t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], n0, n, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
+    dt = time.perf_counter() - t0
+    return n * A * wl["T"] / dt, cores, f"{n} of the workload's trials x T={wl['T']} x A={A} (generation + simulation), {dt:.1f} s"
+
+
+def run_reference(args, wl):
+    """--impl reference: the CPU port of the same sweep, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    A = len(wl["alg"]); cores = O.num_threads()
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    n0 = max(cores, 8)
+    t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"])
+    dt0 = time.perf_counter() - t0
+    n = max(cores, int(n0 * per_step_budget / max(dt0, 1e-6)))
+    for _ in range(args.warmup):
+        O.regret_sweep(0, wl["T"], 0, n, wl["d"], wl["alg"], wl["eta"])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        O.regret_sweep(0, wl["T"], k * n, n, wl["d"], wl["alg"], wl["eta"])
+    dt = time.perf_counter() - t0
+    val = args.steps * n * A * wl["T"] / dt
+    sample = f"{n} trials/step x T={wl['T']} x A={A}, oracle port (C, OpenMP), generation included"
+    print(json.dumps({
+        "impl": "reference", "metric": "trajectory-steps/sec", "value": val, "unit": "trajectory-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "trials_per_step": n, "T": wl["T"], "d": wl["d"], "variants": A},
+        "cpu_baseline": {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--trials", type=int, default=0, help="sequences per GPU per step (default: the workload's)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.trials:
+        wl["trials"] = args.trials
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from online_convex_optimization_b200 import dist as odist
+    from online_convex_optimization_b200 import engine
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, T, d, A = wl["trials"], wl["T"], wl["d"], len(wl["alg"])
+    run_lo = rank * B                                   # weak scaling: every rank owns its own block of runs
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(k):
+        reg, stats = engine.regret_sweep_device("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo)
+        odist.allreduce_stats(stats)
+        return reg, stats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                            # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record()
+        reg, stats = step(k)
+        ev[k][1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    total_steps = float(world) * B * A * T * args.steps
+    value = total_steps / (ms * 1e-3)
+
+    # ---- e2e through the public host API (host args in, regrets + stats back in host memory)
+    e2e_steps = max(1, min(args.steps, 3))
+    engine.regret_sweep("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        out = engine.regret_sweep("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo, device=local)
+        if world > 1:
+            st = torch.from_numpy(out["stats"]).to(dev); odist.allreduce_stats(st); st.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = float(world) * B * A * T * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        st = stats.cpu().numpy()
+        fp64_peak = engine.fp64_peak_ops(local)
+        kernel_steps_per_s = B * A * T * args.steps / (ms * 1e-3)           # this GPU's kernel rate
+        alg_ops = (9 * d + 6)
+        line = {
+            "metric": "trajectory-steps/sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "trials_per_gpu": B, "T": T, "d": d, "variants": A,
+                       "sequence_source": "generated on device from numpy stream keys (base_seed=0, T, run)",
+                       "l2": "256 MiB flush between timed steps; inputs are generated on-chip (no HBM input traffic)",
+                       "parallelism": f"dp{world} (runs sharded, one all-reduce of [A,4] statistics per step)"},
+            "e2e": {"value": e2e_val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": A * 12 + 64,
+                    "d2h_bytes_per_step": B * A * 8 + A * 32, "steps": e2e_steps,
+                    "api": "engine.regret_sweep (oco_regret_sweep_host): per-trajectory regrets + stats to host"},
+            "gpu_launches": args.steps * 3 + (args.steps if world > 1 else 0),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64-pipe", "achieved": kernel_steps_per_s * alg_ops / 1e9, "peak": fp64_peak / 1e9,
+                         "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak, "traffic": None,
+                         "kernel": "sweep_kernel<GPathStream,%d,%d>" % (d, 9 if A > 3 else (3 if A > 1 else 1)),
+                         "algorithmic_ops_per_trajectory_step": alg_ops,
+                         "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)"},
+            "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
+                             "mean_regret_per_variant": [float(v) for v in st[:, 1] / np.maximum(st[:, 3], 1)]},
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, sample = cpu_sweep_rate(wl, args.cpu_budget)
+            line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/*
+ * oco_b200.h -- C ABI of the B200-native engine for the online-convex-optimization hot path
+ * of revvu/online_convex_optimization (FTL / FTRL / SMART trajectory loops + the numpy-keyed
+ * sequence generators).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * The reference is pure Python: its "FFI" for this path is the module seam at
+ * fast_driver.py:23-29 (names imported from fast_algorithms / sequence_generation).  Each
+ * entry point below names the reference function(s) whose per-call work it batches; the
+ * Python module online_convex_optimization_b200.fast_algorithms binds them with ctypes and
+ * re-exports the reference's names and signatures.
+ *
+ * Conventions
+ *   - every function returns an int status (OCO_OK == 0); oco_last_error() gives the message
+ *     of the calling thread's last failure.  OCO_ERR_VALUE maps to Python ValueError,
+ *     OCO_ERR_RUNTIME (CUDA failures) to RuntimeError, mirroring exact_ftl.py:125-126,142-143.
+ *   - sequences are row-major z[B][T][d], y[B][T] (the reference's (T, d) / (T,) arrays,
+ *     fast_algorithms.py:171-177, stacked over B), dtype OCO_F32 or OCO_F64; float32 is
+ *     widened to float64 on load exactly like np.ascontiguousarray(z, dtype=float64).
+ *   - alg_flag: 0 = FTRL, non-zero = FTL (fast_algorithms.py:100-103).  A = number of
+ *     (alg_flag, eta0) variants run on every sequence; results are [B][A] row-major.
+ *   - functions without the _host suffix take DEVICE pointers for bulk data and a
+ *     cudaStream_t (as void*); they enqueue work and return without synchronising.
+ *     alg_flag / eta0 / theta_thresh / keys / T_grid are always small HOST arrays.
+ *   - *_host functions take HOST pointers, perform their own (chunked, double-buffered)
+ *     host<->device copies on `device`, and return after synchronising.
+ *   - the caller owns every buffer; the library frees all scratch it allocates.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with OCO_ERR_RUNTIME.
+ */
+#ifndef OCO_B200_H
+#define OCO_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define OCO_API __attribute__((visibility("default")))
+#else
+#define OCO_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCO_OK 0
+#define OCO_ERR_VALUE 1
+#define OCO_ERR_RUNTIME 2
+
+#define OCO_F32 0
+#define OCO_F64 1
+
+#define OCO_ALG_FTRL 0
+#define OCO_ALG_FTL 1
+
+/* sequence families (sequence_generation.py / fast_algorithms.py:231-239) */
+#define OCO_FAM_GPATH 0   /* standard_normal((T,d)) f64, rows clipped to unit norm, choice([-1,1],T) */
+#define OCO_FAM_IID 1     /* make_random_iid_stream: f32 rows, y = sign(z@u)            (:54-70)  */
+#define OCO_FAM_NOISY 2   /* make_noisy_iid_stream: same + Massart label flips p        (:72-90)  */
+#define OCO_FAM_FLIP 3    /* flip_sequence                                              (:24-28)  */
+#define OCO_FAM_SWITCH 4  /* switching_two_leaders_sequence                             (:36-47)  */
+
+#define OCO_MAX_VARIANTS 64
+#define OCO_MAX_SMART_THRESHOLDS 4
+
+/* comparator_mode for oco_simulate_batch* (d > 8 only; d <= 8 is always exact):
+ * 0 = second pass over the sequence, the literal fast_algorithms.py:113-114;
+ * 1 = single pass using 0.5|z.a - y| = 0.5(1 - y z.a) when ||z_t|| <= 1, y = +-1 (checked per
+ *     row; sequences that violate it fall back to the second pass).  Tolerance 1e-12 relative. */
+#define OCO_COMPARATOR_TWO_PASS 0
+#define OCO_COMPARATOR_LINEAR 1
+
+OCO_API const char* oco_last_error(void);
+OCO_API int oco_abi_version(void);
+/* number of visible CUDA devices (0 and OCO_OK when there is none) */
+OCO_API int oco_device_count(int* count);
+
+/* ---- fast_algorithms.simulate_alg (fast_algorithms.py:171-177 -> _simulate_alg_core :88-115),
+ * batched over B sequences and A variants.  Outputs (device, [B*A] unless noted, any may be
+ * NULL): regret = cum_loss - comp_loss, cum_loss, comp_loss, theta_final [B*A*d],
+ * x_trace [B*A*T*d] (the played iterates x_t; d <= 8 only). */
+OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                       const int* alg_flag, const double* eta0, int A,
+                       double* regret, double* cum_loss, double* comp_loss,
+                       double* theta_final, double* x_trace, int comparator_mode, void* stream);
+OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                            const int* alg_flag, const double* eta0, int A,
+                            double* regret, double* cum_loss, double* comp_loss,
+                            double* theta_final, double* x_trace, int comparator_mode, int device);
+
+/* ---- fast_algorithms.simulate_SMART_like (fast_algorithms.py:184-195 -> :118-164), batched;
+ * A <= OCO_MAX_SMART_THRESHOLDS (theta_thresh[a], eta0[a]) pairs per sequence, d <= 8.
+ * switch_t [B*A] (may be NULL) = step at which the switch test fired, -1 if never. */
+OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                    const double* theta_thresh, const double* eta0, int A,
+                    double* regret, int64_t* switch_t, void* stream);
+OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                         const double* theta_thresh, const double* eta0, int A,
+                         double* regret, int64_t* switch_t, int device);
+
+/* ---- sequence generators (sequence_generation.py:24-100, fast_algorithms.py:231-239).
+ * Sequence b is drawn from np.random.Generator(PCG64(SeedSequence([a_b, T, c_b]))) with
+ * (a_b, c_b) = (keys[2b], keys[2b+1]) when keys != NULL, else (key_a, key_c0 + b).
+ * g-path: a = base_seed, c = run.  iid / noisy: a = run_seed, c = 13 + rep / 23 + rep.
+ * Writes z[B][T][d], y[B][T] in out_dtype (device / host). */
+OCO_API int oco_gen_sequences(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                      int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
+                      int out_dtype, void* z, void* y, void* stream);
+OCO_API int oco_gen_sequences_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                           int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
+                           int out_dtype, void* z, void* y, int device);
+
+/* ---- fused generate + simulate + compare for seeded families GPATH / IID / NOISY, d <= 5:
+ * the sequences never exist in memory.  This is the inner double loop of
+ * fast_algorithms.empirical_worst_case_thresholds (:226-243) and of
+ * fast_driver.evaluate_stream_with_stats (:87-111, FTRL / FTL columns) as one launch.
+ * regret / cum_loss / comp_loss: [B*A] or NULL.  stats: [A*4] = (max, sum, sum of squares,
+ * count) of the regrets per variant, reduced in a fixed order (bit-reproducible), or NULL. */
+OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                     int64_t B, int64_t T, int d, double p_flip,
+                     const int* alg_flag, const double* eta0, int A,
+                     double* regret, double* cum_loss, double* comp_loss, double* stats, void* stream);
+OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                          int64_t B, int64_t T, int d, double p_flip,
+                          const int* alg_flag, const double* eta0, int A,
+                          double* regret, double* cum_loss, double* comp_loss, double* stats, int device);
+
+/* ---- fast_algorithms.empirical_worst_case_thresholds (fast_algorithms.py:211-247) for runs
+ * [run_lo, run_lo + n_runs): g_max[i] = max(0, max_r regret_FTRL(eta0)) on g-path sequences of
+ * length T_grid[i]; stats [nT*4] as above (may be NULL).  d <= 5 (the reference uses 5). */
+OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
+                     int d, double eta0, double* g_max, double* stats, int device);
+
+/* ---- known-answer probes of the device generator (tests): what = 0 raw uint64, 1 standard
+ * normals, 2 random() doubles, 3 choice([-1,1]) labels, 4 SeedSequence state words, 5 log1p(-U);
+ * n_skip normals are consumed first.  out: HOST buffer of n 8-byte items. */
+OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device);
+
+/* ---- roofline denominator for the generated-on-device kernels: measured issue rate of
+ * independent non-fused fp64 multiplies and adds (ops / second) on `device`. */
+OCO_API int oco_fp64_peak_probe_host(int device, double* ops_per_sec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCO_B200_H */

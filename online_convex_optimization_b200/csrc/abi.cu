@@ -1,0 +1,398 @@
+// abi.cu -- the extern "C" boundary declared in include/oco_b200.h.
+// Validates arguments, owns scratch (stream-ordered allocations), picks the kernel family
+// and, for the *_host entry points, runs the chunked double-buffered host<->device pipeline.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oco_b200.h"
+#include "oco_internal.h"
+
+using namespace oco;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return fail(OCO_ERR_RUNTIME, "%s failed: %s", #expr, cudaGetErrorString(e_)); } while (0)
+
+inline size_t elem_size(int dtype) { return dtype == OCO_F32 ? 4 : 8; }
+
+int check_common(const void* z, const void* y, int dtype, int64_t B, int64_t T, int d, int A) {
+    if (dtype != OCO_F32 && dtype != OCO_F64) return fail(OCO_ERR_VALUE, "dtype must be OCO_F32 or OCO_F64");
+    if (B < 0 || T < 0 || d < 1) return fail(OCO_ERR_VALUE, "need B >= 0, T >= 0, d >= 1 (got B=%lld T=%lld d=%d)", (long long)B, (long long)T, d);
+    if (A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need 1 <= A <= %d (got %d)", OCO_MAX_VARIANTS, A);
+    if (B > 0 && T > 0 && (!z || !y)) return fail(OCO_ERR_VALUE, "z / y must not be NULL");
+    return OCO_OK;
+}
+
+int make_variants(const int* alg_flag, const double* eta0, int A, Variants& v, Etas& e) {
+    if (!alg_flag || !eta0) return fail(OCO_ERR_VALUE, "alg_flag / eta0 must not be NULL");
+    v.A = A;
+    for (int a = 0; a < kMaxVariants; ++a) { v.alg_flag[a] = a < A ? alg_flag[a] : 0; e.e[a] = a < A ? eta0[a] : 0.0; }
+    return OCO_OK;
+}
+
+struct DevBuf {           // stream-ordered scratch, freed on the same stream
+    void* p = nullptr; cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t n, cudaStream_t s) { st = s; return cudaMallocAsync(&p, n ? n : 8, s); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    int set(int device) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+            return fail(OCO_ERR_RUNTIME, "no CUDA device: this engine has no CPU fallback");
+        if (device < 0 || device >= n) return fail(OCO_ERR_VALUE, "device %d out of range (have %d)", device, n);
+        CU(cudaGetDevice(&prev));
+        CU(cudaSetDevice(device));
+        ok = true;
+        return OCO_OK;
+    }
+    ~DeviceGuard() { if (ok && prev >= 0) cudaSetDevice(prev); }
+};
+
+struct StreamPair {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    int create() { CU(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking)); return OCO_OK; }
+    ~StreamPair() { for (auto x : s) if (x) cudaStreamDestroy(x); }
+};
+
+int upload_keys(const uint64_t* keys, int64_t B, DevBuf& buf, cudaStream_t st, const uint64_t** out) {
+    *out = nullptr;
+    if (!keys || B <= 0) return OCO_OK;
+    CU(buf.alloc(sizeof(uint64_t) * 2 * (size_t)B, st));
+    CU(cudaMemcpyAsync(buf.p, keys, sizeof(uint64_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, st));
+    *out = buf.as<uint64_t>();
+    return OCO_OK;
+}
+
+int check_family(int family, int d, bool fused) {
+    if (family < OCO_FAM_GPATH || family > OCO_FAM_SWITCH) return fail(OCO_ERR_VALUE, "unknown sequence family %d", family);
+    if (fused) {
+        if (family > OCO_FAM_NOISY) return fail(OCO_ERR_VALUE, "fused sweep supports the seeded families only (got %d)", family);
+        if (d > 5) return fail(OCO_ERR_VALUE, "fused sweep supports d <= 5 (got %d); generate + simulate instead", d);
+    } else if (family <= OCO_FAM_NOISY) {
+        const bool ok = (d >= 1 && d <= 5) || d == 8 || d == 16 || d == 32 || d == 64;
+        if (!ok) return fail(OCO_ERR_VALUE, "generator supports d in {1..5, 8, 16, 32, 64} (got %d)", d);
+    }
+    return OCO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+OCO_API const char* oco_last_error(void) { return g_err.c_str(); }
+OCO_API int oco_abi_version(void) { return 1; }
+
+OCO_API int oco_device_count(int* count) {
+    if (!count) return fail(OCO_ERR_VALUE, "count must not be NULL");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return OCO_OK;
+}
+
+// ---------------------------------------------------------------------------------- simulate
+OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                       const int* alg_flag, const double* eta0, int A,
+                       double* regret, double* cum_loss, double* comp_loss,
+                       double* theta_final, double* x_trace, int comparator_mode, void* stream) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
+    if (d > 256) return fail(OCO_ERR_VALUE, "d <= 256 supported (got %d)", d);
+    if (x_trace && d > kMaxSmallD) return fail(OCO_ERR_VALUE, "x_trace is available for d <= %d only", kMaxSmallD);
+    if (comparator_mode != OCO_COMPARATOR_TWO_PASS && comparator_mode != OCO_COMPARATOR_LINEAR)
+        return fail(OCO_ERR_VALUE, "unknown comparator_mode %d", comparator_mode);
+    Variants v; Etas e;
+    if (int rc = make_variants(alg_flag, eta0, A, v, e)) return rc;
+    if (B == 0) return OCO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf tab;
+    CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
+    CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
+    if (d <= kMaxSmallD)
+        CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, x_trace, st));
+    else
+        CU(launch_sim_wide(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, comparator_mode, st));
+    return OCO_OK;
+}
+
+OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                            const int* alg_flag, const double* eta0, int A,
+                            double* regret, double* cum_loss, double* comp_loss,
+                            double* theta_final, double* x_trace, int comparator_mode, int device) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0) return OCO_OK;
+    StreamPair sp; if (int rc = sp.create()) return rc;
+    const size_t es = elem_size(in_dtype);
+    const size_t seq_bytes = (size_t)T * (d + 1) * es;
+    const size_t out_per_seq = (size_t)A * 8 * (3 + (theta_final ? d : 0) + (x_trace ? (size_t)T * d : 0));
+    // chunk so that one buffer set stays <= ~256 MiB; two sets are in flight
+    int64_t chunk = (int64_t)std::max<size_t>(1, (256u << 20) / std::max<size_t>(1, seq_bytes + out_per_seq));
+    chunk = std::min<int64_t>(chunk, B);
+    DevBuf zd[2], yd[2], rd[2], cd[2], pd[2], td[2], xd[2];
+    for (int i = 0; i < 2; ++i) {
+        cudaStream_t s = sp.s[i];
+        CU(zd[i].alloc((size_t)chunk * T * d * es, s)); CU(yd[i].alloc((size_t)chunk * T * es, s));
+        CU(rd[i].alloc((size_t)chunk * A * 8, s)); CU(cd[i].alloc((size_t)chunk * A * 8, s)); CU(pd[i].alloc((size_t)chunk * A * 8, s));
+        if (theta_final) CU(td[i].alloc((size_t)chunk * A * d * 8, s));
+        if (x_trace) CU(xd[i].alloc((size_t)chunk * A * T * d * 8, s));
+    }
+    int it = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
+        const int i = it & 1; cudaStream_t s = sp.s[i];
+        const int64_t nb = std::min<int64_t>(chunk, B - b0);
+        CU(cudaMemcpyAsync(zd[i].p, (const char*)z + (size_t)b0 * T * d * es, (size_t)nb * T * d * es, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(yd[i].p, (const char*)y + (size_t)b0 * T * es, (size_t)nb * T * es, cudaMemcpyHostToDevice, s));
+        if (int rc = oco_simulate_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, alg_flag, eta0, A,
+                                        rd[i].as<double>(), cd[i].as<double>(), pd[i].as<double>(),
+                                        theta_final ? td[i].as<double>() : nullptr, x_trace ? xd[i].as<double>() : nullptr,
+                                        comparator_mode, s)) return rc;
+        if (regret) CU(cudaMemcpyAsync(regret + b0 * A, rd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
+        if (cum_loss) CU(cudaMemcpyAsync(cum_loss + b0 * A, cd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
+        if (comp_loss) CU(cudaMemcpyAsync(comp_loss + b0 * A, pd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
+        if (theta_final) CU(cudaMemcpyAsync(theta_final + b0 * A * d, td[i].p, (size_t)nb * A * d * 8, cudaMemcpyDeviceToHost, s));
+        if (x_trace) CU(cudaMemcpyAsync(x_trace + b0 * A * T * d, xd[i].p, (size_t)nb * A * T * d * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(sp.s[0])); CU(cudaStreamSynchronize(sp.s[1]));
+    return OCO_OK;
+}
+
+// ---------------------------------------------------------------------------------- SMART
+OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                    const double* theta_thresh, const double* eta0, int A,
+                    double* regret, int64_t* switch_t, void* stream) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
+    if (A > OCO_MAX_SMART_THRESHOLDS) return fail(OCO_ERR_VALUE, "SMART: A <= %d thresholds per call (got %d)", OCO_MAX_SMART_THRESHOLDS, A);
+    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "SMART: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (!theta_thresh || !eta0 || (B > 0 && !regret)) return fail(OCO_ERR_VALUE, "theta_thresh / eta0 / regret must not be NULL");
+    if (B == 0) return OCO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Etas e; for (int a = 0; a < kMaxVariants; ++a) e.e[a] = a < A ? eta0[a] : 0.0;
+    DevBuf tab, th;
+    CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
+    CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
+    CU(th.alloc(sizeof(double) * A, st));
+    CU(cudaMemcpyAsync(th.p, theta_thresh, sizeof(double) * A, cudaMemcpyHostToDevice, st));
+    CU(launch_smart(z, y, in_dtype == OCO_F32, B, T, d, th.as<double>(), tab.as<double>(), A, regret, switch_t, st));
+    return OCO_OK;
+}
+
+OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                         const double* theta_thresh, const double* eta0, int A,
+                         double* regret, int64_t* switch_t, int device) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0) return OCO_OK;
+    StreamPair sp; if (int rc = sp.create()) return rc;
+    const size_t es = elem_size(in_dtype);
+    const size_t seq_bytes = (size_t)T * (d + 1) * es;
+    int64_t chunk = (int64_t)std::max<size_t>(1, (256u << 20) / std::max<size_t>(1, seq_bytes));
+    chunk = std::min<int64_t>(chunk, B);
+    DevBuf zd[2], yd[2], rd[2], sd[2];
+    for (int i = 0; i < 2; ++i) {
+        cudaStream_t s = sp.s[i];
+        CU(zd[i].alloc((size_t)chunk * T * d * es, s)); CU(yd[i].alloc((size_t)chunk * T * es, s));
+        CU(rd[i].alloc((size_t)chunk * A * 8, s)); CU(sd[i].alloc((size_t)chunk * A * 8, s));
+    }
+    int it = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
+        const int i = it & 1; cudaStream_t s = sp.s[i];
+        const int64_t nb = std::min<int64_t>(chunk, B - b0);
+        CU(cudaMemcpyAsync(zd[i].p, (const char*)z + (size_t)b0 * T * d * es, (size_t)nb * T * d * es, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(yd[i].p, (const char*)y + (size_t)b0 * T * es, (size_t)nb * T * es, cudaMemcpyHostToDevice, s));
+        if (int rc = oco_smart_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, theta_thresh, eta0, A, rd[i].as<double>(), sd[i].as<int64_t>(), s)) return rc;
+        CU(cudaMemcpyAsync(regret + b0 * A, rd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
+        if (switch_t) CU(cudaMemcpyAsync(switch_t + b0 * A, sd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(sp.s[0])); CU(cudaStreamSynchronize(sp.s[1]));
+    return OCO_OK;
+}
+
+// ---------------------------------------------------------------------------------- generators
+OCO_API int oco_gen_sequences(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                      int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
+                      int out_dtype, void* z, void* y, void* stream) {
+    if (int rc = check_common(z, y, out_dtype, B, T, d, 1)) return rc;
+    if (int rc = check_family(family, d, false)) return rc;
+    if (family == OCO_FAM_SWITCH && block_len < 1) return fail(OCO_ERR_VALUE, "block_len must be >= 1");
+    if (B == 0 || T == 0) return OCO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf kb; const uint64_t* kd = nullptr;
+    if (int rc = upload_keys(keys, B, kb, st, &kd)) return rc;
+    CU(launch_fill(family, key_a, key_c0, kd, B, T, d, p_flip, block_len, out_dtype == OCO_F32, z, y, st));
+    return OCO_OK;
+}
+
+OCO_API int oco_gen_sequences_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                           int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
+                           int out_dtype, void* z, void* y, int device) {
+    if (int rc = check_common(z, y, out_dtype, B, T, d, 1)) return rc;
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0 || T == 0) return OCO_OK;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t es = elem_size(out_dtype);
+    int rc = OCO_OK;
+    {
+        DevBuf zd, yd;
+        cudaError_t e1 = zd.alloc((size_t)B * T * d * es, st), e2 = yd.alloc((size_t)B * T * es, st);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        if (!rc) rc = oco_gen_sequences(family, key_a, key_c0, keys, B, T, d, p_flip, block_len, out_dtype, zd.p, yd.p, st);
+        if (!rc && (cudaMemcpyAsync(z, zd.p, (size_t)B * T * d * es, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaMemcpyAsync(y, yd.p, (size_t)B * T * es, cudaMemcpyDeviceToHost, st) != cudaSuccess))
+            rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "stream sync failed: %s", cudaGetErrorString(es_));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------- fused sweep
+OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                     int64_t B, int64_t T, int d, double p_flip,
+                     const int* alg_flag, const double* eta0, int A,
+                     double* regret, double* cum_loss, double* comp_loss, double* stats, void* stream) {
+    if (B < 0 || T < 0 || d < 1) return fail(OCO_ERR_VALUE, "need B >= 0, T >= 0, d >= 1");
+    if (A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need 1 <= A <= %d (got %d)", OCO_MAX_VARIANTS, A);
+    if (int rc = check_family(family, d, true)) return rc;
+    Variants v; Etas e;
+    if (int rc = make_variants(alg_flag, eta0, A, v, e)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        if (stats) CU(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * A, st));
+        return OCO_OK;
+    }
+    DevBuf tab, kb, part;
+    CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
+    CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
+    const uint64_t* kd = nullptr;
+    if (int rc = upload_keys(keys, B, kb, st, &kd)) return rc;
+    const int nblocks = sweep_gpath_blocks(B);
+    if (stats) CU(part.alloc(sizeof(double) * 3 * (size_t)nblocks * A, st));
+    CU(launch_sweep(family, key_a, key_c0, kd, T, B, d, p_flip, v, tab.as<double>(), regret, cum_loss, comp_loss,
+                    stats ? part.as<double>() : nullptr, st));
+    if (stats) CU(launch_stats_finalize(part.as<double>(), nblocks, A, B, stats, st));
+    return OCO_OK;
+}
+
+OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                          int64_t B, int64_t T, int d, double p_flip,
+                          const int* alg_flag, const double* eta0, int A,
+                          double* regret, double* cum_loss, double* comp_loss, double* stats, int device) {
+    if (B < 0 || A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need B >= 0 and 1 <= A <= %d", OCO_MAX_VARIANTS);
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = OCO_OK;
+    {
+        DevBuf rd, cd, pd, sd;
+        const size_t n = (size_t)B * A * 8;
+        bool ok = true;
+        if (regret) ok = ok && rd.alloc(n, st) == cudaSuccess;
+        if (cum_loss) ok = ok && cd.alloc(n, st) == cudaSuccess;
+        if (comp_loss) ok = ok && pd.alloc(n, st) == cudaSuccess;
+        if (stats) ok = ok && sd.alloc(sizeof(double) * 4 * A, st) == cudaSuccess;
+        if (!ok) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        if (!rc) rc = oco_regret_sweep(family, key_a, key_c0, keys, B, T, d, p_flip, alg_flag, eta0, A,
+                                       rd.as<double>(), cd.as<double>(), pd.as<double>(), sd.as<double>(), st);
+        if (!rc) {
+            bool c = true;
+            if (regret && n) c = c && cudaMemcpyAsync(regret, rd.p, n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (cum_loss && n) c = c && cudaMemcpyAsync(cum_loss, cd.p, n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (comp_loss && n) c = c && cudaMemcpyAsync(comp_loss, pd.p, n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (stats) c = c && cudaMemcpyAsync(stats, sd.p, sizeof(double) * 4 * A, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (!c) rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+        }
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "sweep failed: %s", cudaGetErrorString(es_));
+    return rc;
+}
+
+OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
+                     int d, double eta0, double* g_max, double* stats, int device) {
+    if (!T_grid || !g_max || nT < 0) return fail(OCO_ERR_VALUE, "T_grid / g_max must not be NULL");
+    if (n_runs < 0) return fail(OCO_ERR_VALUE, "n_runs must be >= 0");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = OCO_OK;
+    std::vector<double> hs((size_t)std::max(nT, 1) * 4, 0.0);
+    {
+        DevBuf sd;
+        if (sd.alloc(sizeof(double) * 4 * (size_t)std::max(nT, 1), st) != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        const int flag = OCO_ALG_FTRL;
+        for (int i = 0; i < nT && !rc; ++i) {
+            if (T_grid[i] < 0) { rc = fail(OCO_ERR_VALUE, "T_grid[%d] < 0", i); break; }
+            rc = oco_regret_sweep(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T_grid[i], d, -1.0, &flag, &eta0, 1,
+                                  nullptr, nullptr, nullptr, sd.as<double>() + 4 * i, st);
+        }
+        if (!rc && nT > 0 && cudaMemcpyAsync(hs.data(), sd.p, sizeof(double) * 4 * nT, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "g sweep failed: %s", cudaGetErrorString(es_));
+    if (rc) return rc;
+    for (int i = 0; i < nT; ++i) {
+        const double mx = n_runs > 0 ? hs[4 * i] : 0.0;
+        g_max[i] = mx > 0.0 ? mx : 0.0;                 // max_regret starts at 0.0 (fast_algorithms.py:228)
+        if (stats) for (int k = 0; k < 4; ++k) stats[4 * i + k] = hs[4 * i + k];
+    }
+    return OCO_OK;
+}
+
+OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device) {
+    if (!out || n < 0 || n_skip < 0 || what < 0 || what > 5) return fail(OCO_ERR_VALUE, "bad rng probe arguments");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (n == 0) return OCO_OK;
+    void* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)n * 8));
+    cudaError_t e = launch_rng_probe(what, a, b, c, n_skip, n, d, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(OCO_ERR_RUNTIME, "rng probe failed: %s", cudaGetErrorString(e));
+    return OCO_OK;
+}
+
+OCO_API int oco_fp64_peak_probe_host(int device, double* ops_per_sec) {
+    if (!ops_per_sec) return fail(OCO_ERR_VALUE, "ops_per_sec must not be NULL");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double* d = nullptr; CU(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0.0; int rc = OCO_OK;
+    for (int rep = 0; rep < 4 && !rc; ++rep) {            // rep 0 is the warm-up
+        cudaEventRecord(e0, nullptr);
+        cudaError_t e = launch_fp64_probe(d, blocks, iters, nullptr);
+        cudaEventRecord(e1, nullptr);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { rc = fail(OCO_ERR_RUNTIME, "fp64 probe failed: %s", cudaGetErrorString(e)); break; }
+        float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = 16.0 * iters * 256.0 * blocks / (ms * 1e-3);
+        if (rep > 0 && ops > best) best = ops;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *ops_per_sec = best;
+    return rc;
+}
+
+}  // extern "C"

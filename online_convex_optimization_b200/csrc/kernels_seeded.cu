@@ -1,0 +1,312 @@
+// kernels_seeded.cu -- sequences generated on the device from their numpy stream keys.
+//
+//  sweep_kernel<Stream, D, AV>   generate + simulate + compare, fused: one thread per
+//      sequence keeps the RNG cursors, AV trajectories' theta / cumulative loss and the
+//      comparator accumulators in registers; the sequence is regenerated for the
+//      comparator pass (fast_algorithms.py:113-114 needs the FINAL theta) instead of
+//      being stored, so the kernel touches HBM only for its 8*A-byte result per sequence.
+//      Bound: fp64 pipe / issue slots, never HBM.
+//  fill_kernel<Stream, D, TOUT>  write the sequences to HBM (z[B][T][d], y[B][T]) for the
+//      streamed kernels (BASELINE config 4) and for callers that want the arrays.
+//  stats_finalize_kernel        fixed-order reduction of the per-block (max, sum, sumsq).
+#include "oco_device.cuh"
+#include "oco_internal.h"
+#include "streams.cuh"
+
+namespace oco {
+
+constexpr int kSweepBlock = 128;
+
+struct SweepArgs {
+    uint64_t key_a;          // first entropy word (base_seed / run_seed) when keys == nullptr
+    uint64_t key_c0;         // third entropy word of sequence 0 (run_lo); sequence b uses key_c0 + b
+    const uint64_t* keys;    // optional device [B][2] explicit (a, c) pairs
+    int64_t T, B;
+    int family;
+    double p_flip;
+    const double* tab;       // [T][A] FTRL scales
+    double* regret; double* cum; double* comp;   // [B][A] or nullptr
+    double* partials;        // [gridDim.x][A][3] or nullptr
+    Variants v;
+};
+
+template <class Stream, int D, int AV>
+__global__ void __launch_bounds__(kSweepBlock) sweep_kernel(const SweepArgs p) {
+    __shared__ ZigTables tb;
+    __shared__ double red[kSweepBlock / 32][3];
+    zig_tables_load(tb);
+
+    const int64_t b = (int64_t)blockIdx.x * kSweepBlock + threadIdx.x;
+    const bool active = b < p.B;
+    const int A = p.v.A;
+    const int v0 = blockIdx.y * AV;
+    const int nv = min(AV, A - v0);
+    typedef typename Stream::elem_t E;
+
+    double regret[AV];
+#pragma unroll
+    for (int v = 0; v < AV; ++v) regret[v] = 0.0;
+
+    if (active) {
+        Stream st;
+        const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
+        const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
+        st.init(tb, ka, p.T, kc, p.p_flip, p.family);
+
+        TrajState<D> s[AV];
+#pragma unroll
+        for (int v = 0; v < AV; ++v) traj_init<D>(s[v]);
+
+        // ---- pass 1: play (fast_algorithms.py:99-111)
+        for (int64_t t = 0; t < p.T; ++t) {
+            E ze[D]; E ye;
+            st.next(tb, t, ze, ye);
+            double z[D], hz[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) { z[j] = (double)ze[j]; hz[j] = 0.5 * z[j]; }
+            const double y = (double)ye;
+            const double* trow = p.tab + t * A + v0;
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                if (v < nv) {
+                    double x[D];
+                    if (p.v.alg_flag[v0 + v] == 0) action_ftrl<D>(s[v].th, __ldg(trow + v), x);
+                    else action_ftl<D>(s[v].th, x);
+                    play_and_update<D>(s[v], x, z, hz, y);
+                }
+            }
+        }
+        // ---- pass 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114)
+        double act[AV][D], comp[AV];
+#pragma unroll
+        for (int v = 0; v < AV; ++v) { action_ftl<D>(s[v].th, act[v]); comp[v] = 0.0; }
+        st.rewind();
+        for (int64_t t = 0; t < p.T; ++t) {
+            E ze[D]; E ye;
+            st.next(tb, t, ze, ye);
+            double z[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) z[j] = (double)ze[j];
+            const double y = (double)ye;
+#pragma unroll
+            for (int v = 0; v < AV; ++v)
+                if (v < nv) comp[v] = comp[v] + nhinge(dot_seq<D>(z, act[v]), y);
+        }
+#pragma unroll
+        for (int v = 0; v < AV; ++v) {
+            if (v < nv) {
+                regret[v] = s[v].cum - comp[v];
+                const int64_t o = b * A + v0 + v;
+                if (p.regret) p.regret[o] = regret[v];
+                if (p.cum) p.cum[o] = s[v].cum;
+                if (p.comp) p.comp[o] = comp[v];
+            }
+        }
+    }
+
+    // ---- per-block (max, sum, sumsq) of the regrets, fixed order -> deterministic
+    if (p.partials) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int v = 0; v < nv; ++v) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < AV; ++k) if (k == v) r = regret[k];
+            double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
+            double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+                sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
+                sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
+            }
+            if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
+                for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
+                double* o = p.partials + ((int64_t)blockIdx.x * A + v0 + v) * 3;
+                o[0] = m; o[1] = s1; o[2] = s2;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void stats_finalize_kernel(const double* __restrict__ partials, int nblocks, int A, int64_t n_runs,
+                                      double* __restrict__ stats) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    double m = -__longlong_as_double(0x7ff0000000000000LL), s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        const double* o = partials + ((int64_t)b * A + a) * 3;
+        m = fmax(m, o[0]); s1 += o[1]; s2 += o[2];
+    }
+    stats[a * 4 + 0] = m; stats[a * 4 + 1] = s1; stats[a * 4 + 2] = s2; stats[a * 4 + 3] = (double)n_runs;
+}
+
+__global__ void ftrl_scale_table_kernel(double* __restrict__ tab, const Etas eta0, int64_t T, int A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * A) return;
+    const int64_t t = i / A; const int a = (int)(i - t * A);
+    int64_t tt = t + 1; if (tt < 1) tt = 1;
+    tab[i] = -(eta0.e[a] / sqrt((double)tt));     // fast_algorithms.py:54, IEEE sqrt and divide
+}
+
+cudaError_t launch_ftrl_scale_table(double* tab, const Etas& eta0, int64_t T, int A, cudaStream_t st) {
+    const int64_t n = T * A;
+    if (n <= 0) return cudaSuccess;
+    ftrl_scale_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tab, eta0, T, A);
+    return cudaGetLastError();
+}
+
+int sweep_gpath_blocks(int64_t n_runs) { return (int)((n_runs + kSweepBlock - 1) / kSweepBlock); }
+
+template <template <int> class StreamT, int D>
+static cudaError_t launch_sweep_d(const SweepArgs& a, cudaStream_t st) {
+    typedef StreamT<D> Stream;
+    const int A = a.v.A;
+    const unsigned gx = (unsigned)((a.B + kSweepBlock - 1) / kSweepBlock);
+    if (A == 1) {
+        sweep_kernel<Stream, D, 1><<<dim3(gx, 1), kSweepBlock, 0, st>>>(a);
+    } else if (A <= 3) {
+        sweep_kernel<Stream, D, 3><<<dim3(gx, 1), kSweepBlock, 0, st>>>(a);
+    } else {
+        sweep_kernel<Stream, D, 9><<<dim3(gx, (A + 8) / 9), kSweepBlock, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <template <int> class StreamT>
+static cudaError_t launch_sweep_s(const SweepArgs& a, int d, cudaStream_t st) {
+    switch (d) {
+    case 1: return launch_sweep_d<StreamT, 1>(a, st);
+    case 2: return launch_sweep_d<StreamT, 2>(a, st);
+    case 3: return launch_sweep_d<StreamT, 3>(a, st);
+    case 4: return launch_sweep_d<StreamT, 4>(a, st);
+    case 5: return launch_sweep_d<StreamT, 5>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
+                         double p_flip, const Variants& v, const double* scale_tab,
+                         double* regret, double* cum, double* comp, double* partials, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    SweepArgs a;
+    a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = T; a.B = B; a.family = family; a.p_flip = p_flip;
+    a.tab = scale_tab; a.regret = regret; a.cum = cum; a.comp = comp; a.partials = partials; a.v = v;
+    if (family == FAM_GPATH) return launch_sweep_s<GPathStream>(a, d, st);
+    if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_s<IidStream>(a, d, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, int64_t n_runs, double* stats, cudaStream_t st) {
+    stats_finalize_kernel<<<(A + 63) / 64, 64, 0, st>>>(partials, nblocks, A, n_runs, stats);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ fill kernels
+struct FillArgs {
+    uint64_t key_a, key_c0; const uint64_t* keys;
+    int64_t T, B; int family; double p_flip; int64_t block_len;
+    void* z; void* y;
+};
+
+template <class Stream, int D, typename TOUT>
+__global__ void __launch_bounds__(128) fill_kernel(const FillArgs p) {
+    __shared__ ZigTables tb;
+    zig_tables_load(tb);
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    typedef typename Stream::elem_t E;
+    Stream st;
+    const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
+    const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
+    st.init(tb, ka, p.T, kc, p.p_flip, p.family);
+    TOUT* z = (TOUT*)p.z + b * p.T * D;
+    TOUT* y = (TOUT*)p.y + b * p.T;
+    for (int64_t t = 0; t < p.T; ++t) {
+        E ze[D]; E ye;
+        st.next(tb, t, ze, ye);
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[t * D + j] = (TOUT)ze[j];
+        y[t] = (TOUT)ye;
+    }
+}
+
+// sequence_generation.py:24-28 (flip) and :36-47 (switching two leaders); any d.
+template <typename TOUT>
+__global__ void fill_pattern_kernel(int family, int64_t B, int64_t T, int d, int64_t block_len, TOUT* z, TOUT* y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int64_t t = i % T;
+    for (int j = 0; j < d; ++j) z[i * d + j] = (TOUT)(j == 0 ? 1.0 : 0.0);
+    if (family == FAM_FLIP) y[i] = (TOUT)(((t + 1) % 2) ? 1.0 : -1.0);
+    else y[i] = (TOUT)(((t / block_len) % 2) ? -1.0 : 1.0);
+}
+
+template <template <int> class StreamT, int D>
+static cudaError_t launch_fill_d(const FillArgs& a, int out_f32, cudaStream_t st) {
+    const unsigned gx = (unsigned)((a.B + 127) / 128);
+    if (out_f32) fill_kernel<StreamT<D>, D, float><<<gx, 128, 0, st>>>(a);
+    else fill_kernel<StreamT<D>, D, double><<<gx, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+template <template <int> class StreamT>
+static cudaError_t launch_fill_s(const FillArgs& a, int d, int out_f32, cudaStream_t st) {
+    switch (d) {
+    case 1: return launch_fill_d<StreamT, 1>(a, out_f32, st);
+    case 2: return launch_fill_d<StreamT, 2>(a, out_f32, st);
+    case 3: return launch_fill_d<StreamT, 3>(a, out_f32, st);
+    case 4: return launch_fill_d<StreamT, 4>(a, out_f32, st);
+    case 5: return launch_fill_d<StreamT, 5>(a, out_f32, st);
+    case 8: return launch_fill_d<StreamT, 8>(a, out_f32, st);
+    case 16: return launch_fill_d<StreamT, 16>(a, out_f32, st);
+    case 32: return launch_fill_d<StreamT, 32>(a, out_f32, st);
+    case 64: return launch_fill_d<StreamT, 64>(a, out_f32, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t B, int64_t T, int d,
+                        double p_flip, int64_t block_len, int out_f32, void* z, void* y, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return cudaSuccess;
+    if (family == FAM_FLIP || family == FAM_SWITCH) {
+        const int64_t n = B * T;
+        if (out_f32) fill_pattern_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(family, B, T, d, block_len, (float*)z, (float*)y);
+        else fill_pattern_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(family, B, T, d, block_len, (double*)z, (double*)y);
+        return cudaGetLastError();
+    }
+    FillArgs a;
+    a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = T; a.B = B; a.family = family; a.p_flip = p_flip;
+    a.block_len = block_len; a.z = z; a.y = y;
+    if (family == FAM_GPATH) return launch_fill_s<GPathStream>(a, d, out_f32, st);
+    if (family == FAM_IID || family == FAM_NOISY) return launch_fill_s<IidStream>(a, d, out_f32, st);
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ RNG probes (known-answer tests)
+__global__ void rng_probe_kernel(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out) {
+    __shared__ ZigTables tb;
+    zig_tables_load(tb);
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Pcg64 s; PcgInc inc;
+    pcg_seed3(s, inc, a, b, c);
+    if (what == 4) {                       // SeedSequence state words
+        uint64_t w[4]; seedseq3(a, b, c, w);
+        for (int i = 0; i < 4 && i < n; ++i) ((uint64_t*)out)[i] = w[i];
+        return;
+    }
+    for (int64_t i = 0; i < n_skip; ++i) zig_skip(tb, s, inc);
+    if (what == 0) for (int64_t i = 0; i < n; ++i) ((uint64_t*)out)[i] = pcg_next64(s, inc);
+    else if (what == 1) for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = zig_normal(tb, s, inc);
+    else if (what == 2) for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = pcg_double(s, inc);
+    else if (what == 3) { LabelCursor lc; lc.s = s; lc.cur = 0; for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = lc.next(i, inc); }
+    else if (what == 5) for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = log1p_glibc_fma(-pcg_double(s, inc));
+}
+cudaError_t launch_rng_probe(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, cudaStream_t st) {
+    rng_probe_kernel<<<1, 32, 0, st>>>(what, a, b, c, n_skip, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace oco

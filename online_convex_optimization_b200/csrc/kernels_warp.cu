@@ -1,0 +1,351 @@
+// kernels_warp.cu -- warp-per-sequence kernels.
+//
+//  sim_wide_kernel<K, TIN>   FTL / FTRL for larger d (d <= 32*K, BASELINE config 4: d = 64):
+//      lane l holds elements l, l+32, ... of theta / x / z_t; dot products and squared
+//      norms are lane-local partial sums (in k order) followed by an xor-butterfly, so
+//      the reduction order differs from the reference's left-to-right sum: parity is
+//      1e-12 relative regret (north_star), not bit-exact.  Rows are read with one
+//      coalesced load per K (512 B per row at d = 64 fp64) and prefetched one step ahead.
+//      This is the HBM-bound path: (d+1)*sizeof(TIN) bytes per trajectory-step.
+//      comparator_mode 0: second pass over the sequence (exact restatement of
+//      fast_algorithms.py:113-114).  comparator_mode 1: single pass -- while playing,
+//      accumulate v = sum_t y_t z_t; when every row satisfies ||z_t||_2 <= 1 and
+//      y_t in {-1,+1} (true for every generator in sequence_generation.py) then
+//      |z_t.a| <= 1 for the unit-norm comparator a and 0.5*|z_t.a - y_t| = 0.5*(1 - y_t z_t.a),
+//      hence comp = 0.5*(T - a.v) with no second read.  Rows violating the
+//      precondition are detected on the fly and the warp falls back to the second pass.
+//
+//  smart_kernel<D, TIN>      single-switch SMART (fast_algorithms.py:118-164), one warp per
+//      sequence, all thresholds of that sequence at once (the FTL trajectory and the
+//      prefix loss of its leader do not depend on the threshold).  The O(t) prefix loss
+//      (fast_algorithms.py:158 -> :79-85) is spread over the lanes (rows i = lane, lane+32,
+//      ...; each row's dot product is the reference's sequential one) and combined by a
+//      butterfly; the FTL / FTRL states are replicated in every lane, bit-identically.
+#include "oco_device.cuh"
+#include "oco_internal.h"
+
+namespace oco {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// ------------------------------------------------------------------ wide d
+struct WideArgs {
+    const void* z; const void* y;
+    int64_t B, T; int d;
+    const double* tab;
+    double* regret; double* cum; double* comp; double* theta_final;
+    int comparator_mode;
+    Variants v;
+};
+
+constexpr int kWideWarps = 8;   // warps per CTA
+
+template <int K, typename TIN>
+__global__ void __launch_bounds__(kWideWarps * 32) sim_wide_kernel(const WideArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * kWideWarps + (threadIdx.x >> 5);
+    const int A = p.v.A;
+    if (w >= p.B * A) return;
+    const int64_t b = w / A; const int a = (int)(w - b * A);
+    const int d = p.d;
+    const bool ftrl = p.v.alg_flag[a] == 0;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * d;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
+
+    double th[K], vy[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { th[k] = 0.0; vy[k] = 0.0; }
+    double cum = 0.0;
+    bool linear_ok = true;
+
+    double zn[K], yn = 0.0;          // prefetched row
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; zn[k] = (p.T > 0 && j < d) ? (double)zb[j] : 0.0; }
+    if (p.T > 0) yn = (double)yb[0];
+
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[K]; const double y = yn;
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = zn[k];
+        if (t + 1 < p.T) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; zn[k] = (j < d) ? (double)zb[(t + 1) * d + j] : 0.0; }
+            yn = (double)yb[t + 1];
+        }
+        double x[K];
+        if (ftrl) {
+            const double sc = __ldg(p.tab + t * A + a);
+            double n2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { x[k] = sc * th[k]; n2 = n2 + x[k] * x[k]; }
+            n2 = warp_sum(n2);
+            if (!(n2 <= 1.0)) {
+                const double fac = 1.0 / sqrt(n2);
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = x[k] * fac;
+            }
+        } else {
+            double n2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) n2 = n2 + th[k] * th[k];
+            n2 = warp_sum(n2);
+            if (n2 == 0.0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = 0.0;
+            } else {
+                const double sc = -(1.0 / sqrt(n2));
+#pragma unroll
+                for (int k = 0; k < K; ++k) x[k] = sc * th[k];
+            }
+        }
+        double q = 0.0, zz = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { q = q + z[k] * x[k]; zz = zz + z[k] * z[k]; }
+        q = warp_sum(q);
+        const double df = q - y;
+        cum = cum + 0.5 * (df < 0.0 ? -df : df);
+        const double g = df > 0.0 ? 0.5 : (df < 0.0 ? -0.5 : 0.0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) th[k] = th[k] + g * z[k];
+        if (p.comparator_mode == 1) {
+            zz = warp_sum(zz);
+            if (!(zz <= 1.0 + 1e-9) || !(y == 1.0 || y == -1.0)) linear_ok = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) vy[k] = vy[k] + y * z[k];
+        }
+    }
+    // comparator = FTL action of the final theta
+    double act[K];
+    {
+        double n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) n2 = n2 + th[k] * th[k];
+        n2 = warp_sum(n2);
+        const double sc = (n2 == 0.0) ? 0.0 : -(1.0 / sqrt(n2));
+#pragma unroll
+        for (int k = 0; k < K; ++k) act[k] = (n2 == 0.0) ? 0.0 : sc * th[k];
+    }
+    double comp = 0.0;
+    if (p.comparator_mode == 1 && linear_ok) {
+        double av = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) av = av + act[k] * vy[k];
+        av = warp_sum(av);
+        comp = 0.5 * ((double)p.T - av);
+    } else {
+        for (int64_t t = 0; t < p.T; ++t) {
+            double q = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; if (j < d) q = q + (double)zb[t * d + j] * act[k]; }
+            q = warp_sum(q);
+            comp = comp + nhinge(q, (double)yb[t]);
+        }
+    }
+    if (lane == 0) {
+        if (p.regret) p.regret[w] = cum - comp;
+        if (p.cum) p.cum[w] = cum;
+        if (p.comp) p.comp[w] = comp;
+    }
+    if (p.theta_final) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; if (j < d) p.theta_final[w * d + j] = th[k]; }
+    }
+}
+
+template <typename TIN>
+static cudaError_t launch_wide_t(const WideArgs& a, cudaStream_t st) {
+    const int64_t nw = a.B * a.v.A;
+    const unsigned gx = (unsigned)((nw + kWideWarps - 1) / kWideWarps);
+    const int K = (a.d + 31) / 32;
+    switch (K) {
+    case 1: sim_wide_kernel<1, TIN><<<gx, kWideWarps * 32, 0, st>>>(a); break;
+    case 2: sim_wide_kernel<2, TIN><<<gx, kWideWarps * 32, 0, st>>>(a); break;
+    case 3: sim_wide_kernel<3, TIN><<<gx, kWideWarps * 32, 0, st>>>(a); break;
+    case 4: sim_wide_kernel<4, TIN><<<gx, kWideWarps * 32, 0, st>>>(a); break;
+    case 5: case 6: case 7: case 8: sim_wide_kernel<8, TIN><<<gx, kWideWarps * 32, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sim_wide(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                            const Variants& v, const double* scale_tab,
+                            double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
+                            cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    WideArgs a;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.d = d; a.tab = scale_tab;
+    a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final;
+    a.comparator_mode = comparator_mode; a.v = v;
+    return in_f32 ? launch_wide_t<float>(a, st) : launch_wide_t<double>(a, st);
+}
+
+// ------------------------------------------------------------------ SMART
+constexpr int kSmartMaxA = 4;
+constexpr int kSmartWarps = 4;
+
+struct SmartArgs {
+    const void* z; const void* y;
+    int64_t B, T;
+    const double* tab;       // [T][A] FTRL scales (eta0 per variant)
+    const double* thresh;    // [A]
+    int A;
+    double* regret; int64_t* switch_t;    // [B][A]
+};
+
+template <int D, typename TIN>
+__global__ void __launch_bounds__(kSmartWarps * 32) smart_kernel(const SmartArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * kSmartWarps + (threadIdx.x >> 5);
+    if (b >= p.B) return;
+    const int A = p.A;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * D;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
+
+    double thl[D];                       // FTL state (always advanced, :140-146)
+    double thr[kSmartMaxA][D];           // FTRL state per threshold, starts at the switch (:148-154)
+    double total[kSmartMaxA], thresh[kSmartMaxA];
+    int64_t sw[kSmartMaxA];
+#pragma unroll
+    for (int j = 0; j < D; ++j) thl[j] = 0.0;
+#pragma unroll
+    for (int a = 0; a < kSmartMaxA; ++a) {
+        total[a] = 0.0; sw[a] = -1; thresh[a] = a < A ? p.thresh[a] : 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) thr[a][j] = 0.0;
+    }
+    double ftl_loss = 0.0;
+    int n_unswitched = A;
+
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[D], hz[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) { z[j] = (double)zb[t * D + j]; hz[j] = 0.5 * z[j]; }
+        const double y = (double)yb[t];
+        double x[D];
+        action_ftl<D>(thl, x);
+        const double pf = dot_seq<D>(z, x);
+        const double dff = pf - y;
+        if (dff > 0.0) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) thl[j] = thl[j] + hz[j];
+        } else if (dff < 0.0) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) thl[j] = thl[j] - hz[j];
+        }
+        const double lf = 0.5 * (dff < 0.0 ? -dff : dff);
+        ftl_loss = ftl_loss + lf;
+#pragma unroll
+        for (int a = 0; a < kSmartMaxA; ++a) {
+            if (a < A) {
+                if (sw[a] >= 0) {
+                    double xr[D];
+                    action_ftrl<D>(thr[a], __ldg(p.tab + t * A + a), xr);
+                    const double pr = dot_seq<D>(z, xr);
+                    const double dr = pr - y;
+                    total[a] = total[a] + 0.5 * (dr < 0.0 ? -dr : dr);
+                    if (dr > 0.0) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) thr[a][j] = thr[a][j] + hz[j];
+                    } else if (dr < 0.0) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) thr[a][j] = thr[a][j] - hz[j];
+                    }
+                } else {
+                    total[a] = total[a] + lf;
+                }
+            }
+        }
+        if (n_unswitched > 0) {
+            double s[D];
+            action_ftl<D>(thl, s);
+            double part = 0.0;
+            for (int64_t i = lane; i <= t; i += 32) {
+                double zi[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) zi[j] = (double)zb[i * D + j];
+                part = part + nhinge(dot_seq<D>(zi, s), (double)yb[i]);
+            }
+            const double s_loss = warp_sum(part);
+#pragma unroll
+            for (int a = 0; a < kSmartMaxA; ++a) {
+                if (a < A && sw[a] < 0 && ftl_loss - s_loss >= thresh[a]) { sw[a] = t; --n_unswitched; }
+            }
+        }
+    }
+    double s[D];
+    action_ftl<D>(thl, s);
+    double part = 0.0;
+    for (int64_t i = lane; i < p.T; i += 32) {
+        double zi[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) zi[j] = (double)zb[i * D + j];
+        part = part + nhinge(dot_seq<D>(zi, s), (double)yb[i]);
+    }
+    const double comp = warp_sum(part);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < kSmartMaxA; ++a) {
+            if (a < A) {
+                p.regret[b * A + a] = total[a] - comp;
+                if (p.switch_t) p.switch_t[b * A + a] = sw[a];
+            }
+        }
+    }
+}
+
+template <typename TIN>
+static cudaError_t launch_smart_t(const SmartArgs& a, int d, cudaStream_t st) {
+    const unsigned gx = (unsigned)((a.B + kSmartWarps - 1) / kSmartWarps);
+    switch (d) {
+    case 1: smart_kernel<1, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 2: smart_kernel<2, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 3: smart_kernel<3, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 4: smart_kernel<4, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 5: smart_kernel<5, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 6: smart_kernel<6, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 7: smart_kernel<7, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    case 8: smart_kernel<8, TIN><<<gx, kSmartWarps * 32, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                         const double* thresh_dev, const double* scale_tab, int A,
+                         double* regret, int64_t* switch_t, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (A < 1 || A > kSmartMaxA) return cudaErrorInvalidValue;
+    SmartArgs a;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.thresh = thresh_dev; a.A = A;
+    a.regret = regret; a.switch_t = switch_t;
+    return in_f32 ? launch_smart_t<float>(a, d, st) : launch_smart_t<double>(a, d, st);
+}
+
+// ------------------------------------------------------------------ fp64 issue-rate probe
+// Roofline denominator for the generated-on-device kernels ("must be
+// microbenchmarked by the build"): 8 independent chains of alternating DMUL / DADD per thread,
+// no FMA (this file is built with -fmad=false), enough warps to saturate the fp64 pipe.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double m, double c) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] = a[k] * m; a[k] = a[k] + c; }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) out[0] = s;   // keep the chains alive
+}
+cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st) {
+    fp64_probe_kernel<<<blocks, 256, 0, st>>>(out, iters, 0.9999999, 1e-7);
+    return cudaGetLastError();
+}
+
+}  // namespace oco

@@ -1,0 +1,65 @@
+// oco_internal.h -- host-side launcher declarations shared by the .cu files and abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace oco {
+
+constexpr int kMaxVariants = 64;   // A, (algorithm, eta0) variants per sequence
+constexpr int kMaxSmallD = 8;      // thread-per-trajectory kernels (registers hold theta)
+
+enum Family {                      // sequence families
+    FAM_GPATH = 0,                 // fast_algorithms.py:231-239  float64
+    FAM_IID = 1,                   // sequence_generation.py:54-70   float32
+    FAM_NOISY = 2,                 // sequence_generation.py:72-90   float32, Massart flips
+    FAM_FLIP = 3,                  // sequence_generation.py:24-28
+    FAM_SWITCH = 4,                // sequence_generation.py:36-47
+};
+
+struct Variants {                  // passed by value to kernels
+    int A;
+    int alg_flag[kMaxVariants];    // 0 = FTRL, non-zero = FTL (fast_algorithms.py:100-103)
+};
+
+struct Etas { double e[kMaxVariants]; };
+
+// tab[t*A + a] = -(eta0[a] / sqrt(max(1, t+1)))
+cudaError_t launch_ftrl_scale_table(double* tab, const Etas& eta0, int64_t T, int A, cudaStream_t st);
+
+// Fused generate + simulate + compare (no HBM traffic for inputs).  Sequence b has
+// stream key SeedSequence([a, T, c]) with (a, c) = keys[b] when keys != NULL (device
+// [B][2]), else (key_a, key_c0 + b).  regret/cum/comp: device [B*A] or NULL.
+// partials: device [blocks * A * 3] (max, sum, sumsq per block) or NULL.
+cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
+                         double p_flip, const Variants& v, const double* scale_tab,
+                         double* regret, double* cum, double* comp, double* partials, cudaStream_t st);
+int sweep_gpath_blocks(int64_t n_runs);
+// stats[a*4 + {0,1,2,3}] = max, sum, sumsq, count over all runs (fixed reduction order)
+cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, int64_t n_runs, double* stats, cudaStream_t st);
+
+// Fill kernels: write the sequences of one family to device memory, row-major
+// z[B][T][d], y[B][T], as float64 (out_f32 == 0) or float32.  Keys as for launch_sweep.
+cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t B, int64_t T, int d,
+                        double p_flip, int64_t block_len, int out_f32, void* z, void* y, cudaStream_t st);
+
+// Streamed simulators on device-resident sequences (z[B][T][d], y[B][T]; f32 or f64).
+cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                              const Variants& v, const double* scale_tab,
+                              double* regret, double* cum, double* comp, double* theta_final, double* x_trace,
+                              cudaStream_t st);
+cudaError_t launch_sim_wide(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                            const Variants& v, const double* scale_tab,
+                            double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
+                            cudaStream_t st);
+// SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).
+cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                         const double* thresh_dev, const double* scale_tab, int A,
+                         double* regret, int64_t* switch_t, cudaStream_t st);
+
+// non-FMA fp64 issue-rate microbenchmark (16 ops per thread per iteration, 256 threads per block)
+cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
+
+// RNG probes for known-answer tests (device out[n])
+cudaError_t launch_rng_probe(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, cudaStream_t st);
+
+}  // namespace oco

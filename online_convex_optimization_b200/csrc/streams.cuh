@@ -1,0 +1,119 @@
+// streams.cuh -- on-device sequence families: one CUDA thread regenerates exactly the
+// (z_t, y_t) rows the reference's numpy generators produce for one stream key.
+//   GPathStream  fast_algorithms.py:231-239      float64 rows, Rademacher labels via choice()
+//   IidStream    sequence_generation.py:54-90    float32 rows, labels sign(z.u), optional Massart flips
+// Both keep a "normal cursor" and a second cursor positioned after all T*d normals
+// (numpy draws every normal first, then the labels / flip uniforms from the same
+// stream), found once per stream by zig_skip(); rewind() restarts both for the
+// comparator pass so that no sequence ever has to be stored.
+#pragma once
+#include "rng_numpy.cuh"
+
+namespace oco {
+
+// numpy add.reduce pairwise summation (loops_utils.h.src) of squares, compile-time length.
+template <int D, typename F>
+__device__ __forceinline__ F np_pairwise_sumsq(const F (&z)[D]) {
+    if constexpr (D < 8) {
+        F r = z[0] * z[0];                 // 0.0 + s0 is exact
+#pragma unroll
+        for (int j = 1; j < D; ++j) r = r + z[j] * z[j];
+        return r;
+    } else {
+        static_assert(D <= 128, "pairwise block only");
+        F r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = z[j] * z[j];
+        constexpr int NB = D - (D % 8);
+#pragma unroll
+        for (int i = 8; i < NB; i += 8)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = r[j] + z[i + j] * z[i + j];
+        F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+        for (int i = NB; i < D; ++i) res = res + z[i] * z[i];
+        return res;
+    }
+}
+
+template <int D>
+struct GPathStream {
+    typedef double elem_t;
+    PcgInc inc;
+    Pcg64 zs, z0, lab0;
+    LabelCursor lab;
+
+    // key = SeedSequence([a, T, c])
+    __device__ __forceinline__ void init(const ZigTables& tb, uint64_t a, int64_t T, uint64_t c, double /*p_flip*/, int /*family*/) {
+        pcg_seed3(zs, inc, a, (uint64_t)T, c);
+        z0 = zs;
+        Pcg64 s = zs;
+        for (int64_t i = 0; i < T * D; ++i) zig_skip(tb, s, inc);
+        lab0 = s;
+        rewind();
+    }
+    __device__ __forceinline__ void rewind() { zs = z0; lab.s = lab0; lab.cur = 0; }
+
+    __device__ __forceinline__ void next(const ZigTables& tb, int64_t t, double (&z)[D], double& y) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = zig_normal(tb, zs, inc);
+        double nrm = sqrt(np_pairwise_sumsq<D, double>(z));
+        double inv = 1.0 / (nrm > 1.0 ? nrm : 1.0);      // z *= 1.0 / np.maximum(norms, 1.0)
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
+        y = lab.next(t, inc);
+    }
+};
+
+template <int D>
+struct IidStream {
+    typedef float elem_t;
+    PcgInc inc;
+    Pcg64 zs, z0, fl, fl0;
+    float u[D];
+    double p_flip;       // < 0: no flips (separable family)
+
+    __device__ __forceinline__ void init(const ZigTables& tb, uint64_t run_seed, int64_t T, uint64_t stream_id, double p, int family) {
+        {   // task vector u: _rng(run_seed, 0, 11 | 21), float32, normalised (sequence_generation.py:55-59)
+            Pcg64 us; PcgInc ui;
+            pcg_seed3(us, ui, run_seed, 0, family == 2 ? 21ull : 11ull);
+#pragma unroll
+            for (int j = 0; j < D; ++j) u[j] = (float)zig_normal(tb, us, ui);
+            double acc = 0.0;        // OpenBLAS sdot tail: float products, double accumulator
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc = acc + (double)(u[j] * u[j]);
+            float n = sqrtf((float)acc);
+            if (n > 0.0f) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) u[j] = u[j] / n;
+            }
+        }
+        p_flip = (family == 2) ? p : -1.0;
+        pcg_seed3(zs, inc, run_seed, (uint64_t)T, stream_id);
+        z0 = zs; fl0 = zs;
+        if (p_flip >= 0.0) {
+            Pcg64 s = zs;
+            for (int64_t i = 0; i < T * D; ++i) zig_skip(tb, s, inc);
+            fl0 = s;
+        }
+        rewind();
+    }
+    __device__ __forceinline__ void rewind() { zs = z0; fl = fl0; }
+
+    __device__ __forceinline__ void next(const ZigTables& tb, int64_t /*t*/, float (&z)[D], float& y) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = (float)zig_normal(tb, zs, inc);
+        float nrm = sqrtf(np_pairwise_sumsq<D, float>(z));
+        if (!(nrm >= 1.0f)) nrm = 1.0f;                  // np.maximum(norms, 1.0, out=norms)
+        float inv = 1.0f / nrm;
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
+        float q = z[0] * u[0];                           // y = sign(z @ u), zeros -> +1
+#pragma unroll
+        for (int j = 1; j < D; ++j) q = q + z[j] * u[j];
+        y = (q < 0.0f) ? -1.0f : 1.0f;
+        if (p_flip >= 0.0) { if (pcg_double(fl, inc) < p_flip) y = -y; }
+    }
+};
+
+}  // namespace oco

@@ -1,0 +1,244 @@
+"""Batched entry points over the C ABI (include/oco_b200.h).
+
+Host API (numpy in / numpy out, copies done by the library's own double-buffered pipeline):
+    simulate_batch, smart_batch, gen_sequences, regret_sweep, g_sweep
+Device API (torch CUDA tensors in / out, enqueued on torch's current stream, no sync):
+    simulate_batch_device, smart_batch_device, gen_sequences_device, regret_sweep_device
+
+Everything here is argument marshalling; the arithmetic is in csrc/*.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (COMPARATOR_LINEAR, COMPARATOR_TWO_PASS, FAM_FLIP, FAM_GPATH, FAM_IID, FAM_NOISY, FAM_SWITCH,
+                   OCO_F32, OCO_F64)
+
+SQRT2 = math.sqrt(2.0)
+FAMILIES = {"gpath": FAM_GPATH, "iid": FAM_IID, "noisy": FAM_NOISY, "flip": FAM_FLIP, "switch": FAM_SWITCH}
+
+
+def _vp(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(None)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _variants(alg_flags, eta0s):
+    af = np.ascontiguousarray(np.atleast_1d(alg_flags), dtype=np.int32)
+    et = np.ascontiguousarray(np.atleast_1d(eta0s), dtype=np.float64)
+    if af.shape != et.shape or af.ndim != 1:
+        raise ValueError("alg_flags and eta0s must be 1-D and of equal length")
+    return af, et
+
+
+def _prep_zy(z, y):
+    z = np.asarray(z)
+    y = np.asarray(y)
+    if z.dtype == np.float32 and y.dtype == np.float32:
+        dt = np.float32
+    else:
+        dt = np.float64
+    z = np.ascontiguousarray(z, dtype=dt)
+    y = np.ascontiguousarray(y, dtype=dt)
+    if z.ndim == 2:
+        z = z[None]
+        y = y[None]
+    if z.ndim != 3 or y.ndim != 2 or y.shape != z.shape[:2]:
+        raise ValueError(f"expected z (B,T,d) and y (B,T); got {z.shape} and {y.shape}")
+    return z, y, (OCO_F32 if dt == np.float32 else OCO_F64)
+
+
+def _keys(keys, B):
+    if keys is None:
+        return None
+    k = np.ascontiguousarray(keys, dtype=np.uint64)
+    if k.shape != (B, 2):
+        raise ValueError(f"keys must have shape ({B}, 2)")
+    return k
+
+
+# ----------------------------------------------------------------------------- host API
+def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = False,
+                   comparator: str = "two_pass", device: int = 0):
+    """Batched fast_algorithms.simulate_alg: z (B,T,d), y (B,T) -> regret (B,A).
+    full=True returns a dict with cum_loss, comp_loss, theta (B,A,d) [and x_trace (B,A,T,d)]."""
+    z, y, dt = _prep_zy(z, y)
+    B, T, d = z.shape
+    af, et = _variants(alg_flags, eta0s)
+    A = af.size
+    reg = np.empty((B, A))
+    cum = np.empty((B, A)) if full else None
+    comp = np.empty((B, A)) if full else None
+    th = np.empty((B, A, d)) if full else None
+    xt = np.empty((B, A, T, d)) if trace else None
+    mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
+    _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(af), _vp(et), A,
+                                                   _vp(reg), _vp(cum), _vp(comp), _vp(th), _vp(xt), mode, device))
+    if not full and not trace:
+        return reg
+    return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th, "x_trace": xt}
+
+
+def smart_batch(z, y, theta_threshs, eta0s, *, device: int = 0):
+    """Batched fast_algorithms.simulate_SMART_like -> (regret (B,A), switch_t (B,A))."""
+    z, y, dt = _prep_zy(z, y)
+    B, T, d = z.shape
+    th = np.ascontiguousarray(np.atleast_1d(theta_threshs), dtype=np.float64)
+    et = np.ascontiguousarray(np.atleast_1d(eta0s), dtype=np.float64)
+    if th.shape != et.shape or th.ndim != 1:
+        raise ValueError("theta_threshs and eta0s must be 1-D and of equal length")
+    A = th.size
+    reg = np.empty((B, A))
+    sw = np.empty((B, A), dtype=np.int64)
+    _lib.check(_lib.load().oco_smart_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(th), _vp(et), A, _vp(reg), _vp(sw), device))
+    return reg, sw
+
+
+def gen_sequences(family, B: int, T: int, d: int = 5, *, key_a: int = 0, key_c0: int = 0, keys=None,
+                  p_flip: float = -1.0, block_len: int = 20, dtype=None, device: int = 0):
+    """Sequences of one family as numpy arrays z (B,T,d), y (B,T) (see oco_gen_sequences)."""
+    fam = FAMILIES[family] if isinstance(family, str) else int(family)
+    if dtype is None:
+        dtype = np.float64 if fam == FAM_GPATH else np.float32
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("dtype must be float32 or float64")
+    z = np.empty((B, T, d), dtype=dtype)
+    y = np.empty((B, T), dtype=dtype)
+    k = _keys(keys, B)
+    _lib.check(_lib.load().oco_gen_sequences_host(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), block_len,
+                                                  OCO_F32 if dtype == np.float32 else OCO_F64, _vp(z), _vp(y), device))
+    return z, y
+
+
+def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int = 0, key_c0: int = 0, keys=None,
+                 p_flip: float = -1.0, want_regret: bool = True, full: bool = False, device: int = 0):
+    """Fused generate+simulate+compare.  Returns dict(regret (B,A) | None, stats (A,4) = max,sum,sumsq,count
+    [, cum_loss, comp_loss])."""
+    fam = FAMILIES[family] if isinstance(family, str) else int(family)
+    af, et = _variants(alg_flags, eta0s)
+    A = af.size
+    reg = np.empty((B, A)) if want_regret else None
+    cum = np.empty((B, A)) if full else None
+    comp = np.empty((B, A)) if full else None
+    stats = np.zeros((A, 4))
+    k = _keys(keys, B)
+    _lib.check(_lib.load().oco_regret_sweep_host(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
+                                                 _vp(reg), _vp(cum), _vp(comp), _vp(stats), device))
+    return {"regret": reg, "stats": stats, "cum_loss": cum, "comp_loss": comp}
+
+
+def g_sweep(T_grid, *, runs: int, base_seed: int = 0, run_lo: int = 0, d: int = 5, eta0: float = SQRT2, device: int = 0):
+    """empirical_worst_case_thresholds for runs [run_lo, run_lo+runs) -> (g_max (nT,), stats (nT,4))."""
+    tg = np.ascontiguousarray(T_grid, dtype=np.int64)
+    g = np.zeros(tg.size)
+    st = np.zeros((tg.size, 4))
+    _lib.check(_lib.load().oco_g_sweep_host(_vp(tg), tg.size, run_lo, runs, base_seed, d, float(eta0), _vp(g), _vp(st), device))
+    return g, st
+
+
+def rng_probe(what: int, key, n: int, n_skip: int = 0, device: int = 0):
+    out = np.zeros(n, dtype=np.uint64 if what in (0, 4) else np.float64)
+    _lib.check(_lib.load().oco_rng_probe_host(what, int(key[0]), int(key[1]), int(key[2]), n_skip, n, _vp(out), device))
+    return out
+
+
+def fp64_peak_ops(device: int = 0) -> float:
+    """Measured issue rate (ops/s) of independent, non-fused fp64 multiplies and adds."""
+    v = C.c_double(0.0)
+    _lib.check(_lib.load().oco_fp64_peak_probe_host(device, C.byref(v)))
+    return v.value
+
+
+# ----------------------------------------------------------------------------- device API (torch)
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: online_convex_optimization_b200 has no CPU fallback")
+    return torch
+
+
+def _stream_ptr(torch) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dptr(t) -> C.c_void_p:
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, comparator: str = "two_pass"):
+    """z (B,T,d), y (B,T): contiguous CUDA tensors (float32 or float64).  Returns CUDA tensors."""
+    torch = _torch()
+    if z.dtype != y.dtype or z.dtype not in (torch.float32, torch.float64):
+        raise ValueError("z and y must both be float32 or float64")
+    if not (z.is_cuda and y.is_cuda and z.is_contiguous() and y.is_contiguous()):
+        raise ValueError("z and y must be contiguous CUDA tensors")
+    B, T, d = z.shape
+    af, et = _variants(alg_flags, eta0s)
+    A = af.size
+    reg = torch.empty((B, A), dtype=torch.float64, device=z.device)
+    cum = torch.empty_like(reg) if full else None
+    comp = torch.empty_like(reg) if full else None
+    th = torch.empty((B, A, d), dtype=torch.float64, device=z.device) if full else None
+    mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
+                                                  B, T, d, _vp(af), _vp(et), A, _dptr(reg), _dptr(cum), _dptr(comp),
+                                                  _dptr(th), None, mode, _stream_ptr(torch)))
+    if not full:
+        return reg
+    return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th}
+
+
+def smart_batch_device(z, y, theta_threshs, eta0s):
+    torch = _torch()
+    B, T, d = z.shape
+    th = np.ascontiguousarray(np.atleast_1d(theta_threshs), dtype=np.float64)
+    et = np.ascontiguousarray(np.atleast_1d(eta0s), dtype=np.float64)
+    A = th.size
+    reg = torch.empty((B, A), dtype=torch.float64, device=z.device)
+    sw = torch.empty((B, A), dtype=torch.int64, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().oco_smart_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
+                                               B, T, d, _vp(th), _vp(et), A, _dptr(reg), _dptr(sw), _stream_ptr(torch)))
+    return reg, sw
+
+
+def gen_sequences_device(family, B: int, T: int, d: int = 5, *, key_a: int = 0, key_c0: int = 0, keys=None,
+                         p_flip: float = -1.0, block_len: int = 20, dtype=None, device=None):
+    torch = _torch()
+    fam = FAMILIES[family] if isinstance(family, str) else int(family)
+    if dtype is None:
+        dtype = torch.float64 if fam == FAM_GPATH else torch.float32
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    z = torch.empty((B, T, d), dtype=dtype, device=dev)
+    y = torch.empty((B, T), dtype=dtype, device=dev)
+    k = _keys(keys, B)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().oco_gen_sequences(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), block_len,
+                                                 OCO_F32 if dtype == torch.float32 else OCO_F64, _dptr(z), _dptr(y),
+                                                 _stream_ptr(torch)))
+    return z, y
+
+
+def regret_sweep_device(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int = 0, key_c0: int = 0, keys=None,
+                        p_flip: float = -1.0, want_regret: bool = True, device=None):
+    """Returns (regret (B,A) CUDA tensor or None, stats (A,4) CUDA tensor); enqueued, not synchronised."""
+    torch = _torch()
+    fam = FAMILIES[family] if isinstance(family, str) else int(family)
+    af, et = _variants(alg_flags, eta0s)
+    A = af.size
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    reg = torch.empty((B, A), dtype=torch.float64, device=dev) if want_regret else None
+    stats = torch.empty((A, 4), dtype=torch.float64, device=dev)
+    k = _keys(keys, B)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().oco_regret_sweep(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
+                                                _dptr(reg), None, None, _dptr(stats), _stream_ptr(torch)))
+    return reg, stats

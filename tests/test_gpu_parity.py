@@ -1,0 +1,261 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI / the drop-in Python
+modules, against (a) golden vectors produced by running the reference (tests/golden) and
+(b) the CPU oracle on the same seeded inputs.  Bit-exact wherever the summation order is the
+reference's (every d <= 8 kernel and the whole device generator); 1e-12 relative for the
+warp-parallel reductions (d > 8, SMART prefix loss) as north_star states."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import hexf, make_sequence
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+R2 = math.sqrt(2.0)
+REL = 1e-12   # north_star tolerance where the reduction order changes
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from online_convex_optimization_b200 import engine
+    return engine
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+# ------------------------------------------------------------------ device generator
+def test_device_rng_known_answers(eng, golden_rng):
+    g = golden_rng
+    for i, key in enumerate(g["keys"]):
+        key = tuple(int(v) for v in key)
+        assert (eng.rng_probe(4, key, 4) == g[f"state_{i}"]).all()
+        assert (eng.rng_probe(0, key, 64) == g[f"raw_{i}"]).all()
+        assert (bits(eng.rng_probe(1, key, 4096)) == bits(g[f"normal_{i}"])).all()
+        assert (eng.rng_probe(2, key, 256) == g[f"random_{i}"]).all()
+        assert (eng.rng_probe(3, key, 257, n_skip=333) == g[f"choice_after_333_{i}"]).all()
+
+
+def test_device_rng_tail_and_log1p(eng, golden_rng):
+    x = eng.rng_probe(1, (11, 22, 33), 2_000_000)
+    pos = golden_rng["tail_pos"]
+    assert (bits(x[pos]) == bits(golden_rng["tail_val"])).all()
+    assert np.bitwise_xor.reduce(bits(x)) == golden_rng["long_sum_bits"][0]
+    u = O.rng_doubles((3, 4, 5), 20000)
+    assert (bits(eng.rng_probe(5, (3, 4, 5), 20000)) == bits(O.log1p(-u))).all()
+
+
+@pytest.mark.parametrize("d", [1, 2, 5, 8, 64])
+def test_gen_gpath_bit_exact(eng, d):
+    T = 257 if d < 64 else 96
+    z, y = eng.gen_sequences("gpath", 5, T, d, key_a=3, key_c0=7)
+    for b in range(5):
+        zo, yo = O.gen_gpath(3, T, 7 + b, d)
+        assert (bits(z[b]) == bits(zo)).all() and (y[b] == yo).all()
+    z32, y32 = eng.gen_sequences("gpath", 2, T, d, key_a=3, key_c0=7, dtype=np.float32)
+    assert (z32[1] == O.gen_gpath(3, T, 8, d)[0].astype(np.float32)).all()
+
+
+def test_gen_case_families_bit_exact(eng):
+    T = 300
+    keys = np.array([[2025, 13], [2025, 14], [4050, 13], [6075, 20]], dtype=np.uint64)
+    z, y = eng.gen_sequences("iid", 4, T, 5, keys=keys)
+    for b, (rs, st) in enumerate(keys):
+        zo, yo, _ = O.gen_iid(int(rs), T, int(st) - 13)
+        assert (z[b].view(np.uint32) == zo.view(np.uint32)).all() and (y[b] == yo).all()
+    keys[:, 1] += 10
+    z, y = eng.gen_sequences("noisy", 4, T, 5, keys=keys, p_flip=0.10)
+    for b, (rs, st) in enumerate(keys):
+        zo, yo, _ = O.gen_iid(int(rs), T, int(st) - 23, noisy_p=0.10)
+        assert (z[b].view(np.uint32) == zo.view(np.uint32)).all() and (y[b] == yo).all()
+    z, y = eng.gen_sequences("flip", 2, 101, 5)
+    zo, yo, _ = O.gen_flip(101)
+    assert (z[1] == zo).all() and (y[1] == yo).all()
+    z, y = eng.gen_sequences("switch", 1, 333, 5, block_len=20)
+    zo, yo, _ = O.gen_switching(333)
+    assert (z[0] == zo).all() and (y[0] == yo).all()
+
+
+# ------------------------------------------------------------------ FTL / FTRL
+def test_simulate_alg_golden_bit_exact(eng, golden_sim):
+    """Every golden case of d <= 8 through the C ABI: results equal the reference's bit for bit."""
+    n = 0
+    for case in golden_sim["cases"]:
+        if case["d"] > 8:
+            continue
+        z, y = make_sequence(case["spec"])
+        flags, etas, want = [], [], []
+        for k, v in case["results"].items():
+            if k.startswith("alg"):
+                flags.append(int(k[3])); etas.append(float(k.split("eta")[1])); want.append(hexf(v))
+        got = eng.simulate_batch(z, y, flags, etas)[0]
+        assert (bits(got) == bits(np.array(want))).all(), case["name"]
+        n += len(want)
+    assert n > 200
+
+
+def test_simulate_alg_wide_d_tolerance(eng, golden_sim):
+    for case in golden_sim["cases"]:
+        if case["d"] <= 8:
+            continue
+        z, y = make_sequence(case["spec"])
+        flags, etas, want = [], [], []
+        for k, v in case["results"].items():
+            if k.startswith("alg"):
+                flags.append(int(k[3])); etas.append(float(k.split("eta")[1])); want.append(hexf(v))
+        want = np.array(want)
+        for mode in ("two_pass", "linear"):
+            got = eng.simulate_batch(z, y, flags, etas, comparator=mode)[0]
+            assert np.all(np.abs(got - want) <= REL * np.abs(want)), (case["name"], mode, got, want)
+
+
+def test_iterates_bit_exact(eng, golden_iter):
+    """BASELINE config 2's 'bit-exact iterate check': played x_t and final theta, d = 1 and d = 5."""
+    for name in ("d1", "d5"):
+        b, T, r, d = (int(v) for v in golden_iter[f"{name}_key"])
+        z, y = O.gen_gpath(b, T, r, d)
+        res = eng.simulate_batch(z, y, [0, 1], [R2, R2], full=True, trace=True)
+        for a, flag in enumerate((0, 1)):
+            assert (bits(res["x_trace"][0, a]) == bits(golden_iter[f"{name}_alg{flag}_x"])).all()
+            assert (bits(res["theta"][0, a]) == bits(golden_iter[f"{name}_alg{flag}_theta"])).all()
+
+
+@pytest.mark.parametrize("d,T,B", [(1, 1000, 37), (3, 200, 130), (5, 1000, 300), (8, 64, 5), (5, 1, 3), (2, 7, 129)])
+def test_simulate_batch_vs_oracle(eng, d, T, B):
+    rng = np.random.default_rng(d * 1000 + T)
+    z = rng.standard_normal((B, T, d)) * 0.7          # NOT clipped: exercises |q| > 1 and projection
+    y = rng.choice([-1.0, 1.0, 0.0, 0.5], size=(B, T))
+    flags = [0, 1, 0, 0, 1, 0, 0]
+    etas = [R2, R2, 0.1, 10.0, 3.0, 1.0, 0.3]
+    want = O.simulate_batch(z, y, flags, etas, full=True)
+    got = eng.simulate_batch(z, y, flags, etas, full=True)
+    for k in ("regret", "cum_loss", "comp_loss", "theta"):
+        assert (bits(got[k]) == bits(want[k])).all(), k
+    z32, y32 = z.astype(np.float32), y.astype(np.float32)
+    assert (bits(eng.simulate_batch(z32, y32, flags[:2], etas[:2])) == bits(O.simulate_batch(z32, y32, flags[:2], etas[:2]))).all()
+
+
+def test_simulate_wide_vs_oracle(eng):
+    for d, T, B in ((64, 400, 9), (33, 100, 4), (100, 50, 3), (16, 300, 5)):
+        zs, ys = zip(*[O.gen_gpath(5, T, r, d) for r in range(B)])
+        z, y = np.stack(zs), np.stack(ys)
+        flags, etas = [0, 1, 0], [R2, R2, 0.2]
+        want = O.simulate_batch(z, y, flags, etas)
+        for mode in ("two_pass", "linear"):
+            got = eng.simulate_batch(z, y, flags, etas, comparator=mode)
+            assert np.all(np.abs(got - want) <= REL * np.abs(want)), (d, mode)
+        # rows outside the unit ball: linear mode must detect it and fall back
+        z2 = z * 3.0
+        want2 = O.simulate_batch(z2, y, flags, etas)
+        got2 = eng.simulate_batch(z2, y, flags, etas, comparator="linear")
+        assert np.all(np.abs(got2 - want2) <= REL * np.abs(want2))
+
+
+# ------------------------------------------------------------------ SMART
+def test_smart_golden(eng, golden_sim):
+    n = 0
+    for case in golden_sim["cases"]:
+        ths = [k for k in case["results"] if k.startswith("smart_th")]
+        if not ths or case["d"] > 8:
+            continue
+        z, y = make_sequence(case["spec"])
+        th = [float(k[len("smart_th"):]) for k in ths]
+        want = np.array([hexf(case["results"][k]) for k in ths])
+        got, sw = eng.smart_batch(z, y, th, [R2] * len(th))
+        assert np.all(np.abs(got[0] - want) <= REL * np.maximum(np.abs(want), 1.0)), (case["name"], got, want)
+        for a, t in enumerate(th):
+            assert sw[0, a] == O.simulate_smart_like(z, y, t, R2, full=True)["switch_t"]
+        if case["spec"]["family"] in ("Label flips", "Switching leaders"):
+            assert (bits(got[0]) == bits(want)).all()    # dyadic data: any summation order is exact
+        n += len(th)
+    assert n > 60
+
+
+# ------------------------------------------------------------------ fused seeded sweep
+@pytest.mark.parametrize("d,T,B,A", [(1, 500, 200, 9), (5, 300, 150, 1), (5, 200, 140, 2), (2, 100, 10, 4), (5, 100, 130, 9)])
+def test_regret_sweep_bit_exact(eng, d, T, B, A):
+    flags = ([1] + [0] * 8)[:A]
+    etas = [R2 * s for s in (1.0, 0.125, 0.25, 0.5, 1.0, 2.0, 4.0, 8.0, 16.0)][:A]
+    want = O.regret_sweep(7, T, 11, B, d, flags, etas)
+    got = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=7, key_c0=11)
+    assert (bits(got["regret"]) == bits(want)).all()
+    st = got["stats"]
+    assert (st[:, 0] == want.max(axis=0)).all() and (st[:, 3] == B).all()
+    assert np.allclose(st[:, 1], want.sum(axis=0), rtol=1e-13) and np.allclose(st[:, 2], (want ** 2).sum(axis=0), rtol=1e-13)
+
+
+def test_regret_sweep_case_families(eng):
+    T = 200
+    keys = np.array([[2025 * (r + 1), 13 + rep] for r in range(3) for rep in range(4)], dtype=np.uint64)
+    got = eng.regret_sweep("iid", len(keys), T, 5, [0, 1], [R2, R2], keys=keys)["regret"]
+    for b, (rs, st) in enumerate(keys):
+        z, y, _ = O.gen_iid(int(rs), T, int(st) - 13)
+        assert got[b, 0] == O.simulate_alg(z, y, 0, R2) and got[b, 1] == O.simulate_alg(z, y, 1, R2)
+    keys[:, 1] += 10
+    got = eng.regret_sweep("noisy", len(keys), T, 5, [0, 1], [R2, R2], keys=keys, p_flip=0.10)["regret"]
+    for b, (rs, st) in enumerate(keys):
+        z, y, _ = O.gen_iid(int(rs), T, int(st) - 23, noisy_p=0.10)
+        assert got[b, 0] == O.simulate_alg(z, y, 0, R2) and got[b, 1] == O.simulate_alg(z, y, 1, R2)
+
+
+def test_empirical_thresholds_golden(eng, golden_stats):
+    """The reference's own g(T) table (fast_driver default: runs=1000, T=100..1000), bit for bit."""
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    full = {int(k): hexf(v) for k, v in golden_stats["g_emp_runs1000"].items()}
+    assert fa.empirical_worst_case_thresholds(np.arange(100, 1100, 100), runs=1000, base_seed=0) == full
+    small = {int(k): hexf(v) for k, v in golden_stats["g_emp_runs5_seed3"].items()}
+    assert fa.empirical_worst_case_thresholds(np.array([100, 200, 300]), runs=5, base_seed=3) == small
+
+
+# ------------------------------------------------------------------ drop-in module + edges
+def test_dropin_module_signatures(golden_sim):
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    from online_convex_optimization_b200 import sequence_generation as sg
+    case = next(c for c in golden_sim["cases"] if c["name"].startswith("case_Massart"))
+    spec = case["spec"]
+    sampler = sg.CASES[spec["family"]](run_seed=spec["run_seed"])
+    z, y, u = sampler(spec["T"], spec["rep"])
+    assert z.dtype == np.float32 and y.dtype == np.float32 and u.shape == (5,)
+    assert fa.simulate_alg(z, y, alg_flag=0, eta0=R2) == hexf(case["results"][f"alg0_eta{R2!r}"])
+    assert fa.simulate_alg(z, y, alg_flag=1, eta0=R2) == hexf(case["results"][f"alg1_eta{R2!r}"])
+    want = hexf(case["results"][f"smart_th{math.sqrt(2 * spec['T'])!r}"])
+    assert abs(fa.simulate_SMART(z, y) - want) <= REL * max(1.0, abs(want))
+    want = hexf(case["results"]["smart_th3.0"])
+    assert abs(fa.simulate_empirical_g_SMART(z, y, 3.0) - want) <= REL * max(1.0, abs(want))
+    assert sg.RUNS_BY_TITLE["Massart noise 10%"] == 48 and sg.REPLICATES_BY_TITLE["Massart noise 10%"] == 20
+    assert isinstance(fa._rng(0, 1, 2), np.random.Generator)
+
+
+def test_edge_cases(eng):
+    assert eng.simulate_batch(np.zeros((0, 5, 3)), np.zeros((0, 5)), [0], [1.0]).shape == (0, 1)
+    r = eng.simulate_batch(np.zeros((2, 0, 3)), np.zeros((2, 0)), [0, 1], [1.0, 1.0])
+    assert (r == 0.0).all()
+    r = eng.simulate_batch(np.zeros((3, 4, 2)), np.zeros((3, 4)), [0, 1], [1.0, 1.0])   # all-zero rows: q == y
+    assert (r == 0.0).all()
+    got = eng.regret_sweep("gpath", 0, 10, 5, [0], [1.0])
+    assert got["regret"].shape == (0, 1)
+    g, _ = eng.g_sweep([10, 20], runs=0)
+    assert (g == 0.0).all()
+    with pytest.raises(ValueError):
+        eng.simulate_batch(np.zeros((2, 4, 3)), np.zeros((2, 5)), [0], [1.0])
+    with pytest.raises(ValueError):
+        eng.simulate_batch(np.zeros((2, 4, 300)), np.zeros((2, 4)), [0], [1.0])
+    with pytest.raises(ValueError):
+        eng.smart_batch(np.zeros((1, 4, 3)), np.zeros((1, 4)), [1.0] * 5, [1.0] * 5)
+    with pytest.raises(ValueError):
+        eng.regret_sweep("gpath", 4, 10, 6, [0], [1.0])
+
+
+def test_full_size_properties(eng):
+    """BASELINE-size (T = 1e4) checks that do not need the oracle: determinism, independence of
+    batch position / grid shape, and the closed form FTL regret on label flips (T/4)."""
+    T, B = 10_000, 2048
+    a = eng.regret_sweep("gpath", B, T, 1, [1, 0, 0], [R2, R2, 0.5], key_a=0, key_c0=0)["regret"]
+    b = eng.regret_sweep("gpath", 300, T, 1, [0], [R2], key_a=0, key_c0=1000)["regret"]
+    assert (bits(a[1000:1300, 1]) == bits(b[:, 0])).all()
+    assert (bits(a[:4]) == bits(O.regret_sweep(0, T, 0, 4, 1, [1, 0, 0], [R2, R2, 0.5]))).all()
+    z, y = eng.gen_sequences("flip", 1, T, 5)
+    assert eng.simulate_batch(z, y, [1], [R2])[0, 0] == T / 4

@@ -203,52 +203,72 @@ __device__ inline double log1p_glibc_fma(double x) {
 #define OCO_ZIG_R 3.6541528853610087963519472518
 #define OCO_ZIG_INV_R 0.27366123732975827203338247596
 
-// Slow path of random_standard_normal for a raw that failed the `rabs < ki` test.
-// Returns true and sets x if the draw is accepted; false = restart with a new raw.
-__device__ __noinline__ bool zig_slow(const ZigTables& tb, Pcg64& s, const PcgInc& inc,
-                                      int idx, uint64_t rabs, double& x) {
-    if (idx == 0) {
-        for (;;) {
-            double xx = -OCO_ZIG_INV_R * log1p_glibc_fma(-pcg_double(s, inc));
-            double yy = -log1p_glibc_fma(-pcg_double(s, inc));
-            if (yy + yy > xx * xx) {
-                x = ((rabs >> 8) & 1) ? -(OCO_ZIG_R + xx) : OCO_ZIG_R + xx;
-                return true;
+// Slow path of random_standard_normal: entered with a raw that failed the `rabs < ki` test and
+// left only with an accepted normal, i.e. the whole rejection loop (wedge test, tail sampler,
+// redraws) lives in this one non-inlined function.  The caller's per-step code therefore
+// contains no loop at all -- nvcc 12.9 otherwise merges the rejection loop into the caller's
+// uniform-counter time loop and lanes that redraw lose a step (observed on sm_100a).
+// State goes in and out by value so that the fast path keeps it in registers.
+struct ZigSlowRet { double x; uint64_t hi, lo; };
+
+__device__ __noinline__ ZigSlowRet zig_slow(const ZigTables* tb, uint64_t s_hi, uint64_t s_lo,
+                                            uint64_t inc_hi, uint64_t inc_lo, int idx, uint64_t rabs, double x) {
+    Pcg64 s; s.hi = s_hi; s.lo = s_lo;
+    PcgInc inc; inc.hi = inc_hi; inc.lo = inc_lo;
+    ZigSlowRet out;
+    for (;;) {
+        if (idx == 0) {
+            for (;;) {
+                double xx = -OCO_ZIG_INV_R * log1p_glibc_fma(-pcg_double(s, inc));
+                double yy = -log1p_glibc_fma(-pcg_double(s, inc));
+                if (yy + yy > xx * xx) {
+                    out.x = ((rabs >> 8) & 1) ? -(OCO_ZIG_R + xx) : OCO_ZIG_R + xx;
+                    out.hi = s.hi; out.lo = s.lo;
+                    return out;
+                }
             }
         }
+        double f1 = tb->fi[idx], f0 = tb->fi[idx - 1];
+        // exp() here only feeds a comparison; a 1-ulp difference from glibc's exp flips
+        // the outcome with probability ~2^-52 per wedge test (documented in DESIGN.md).
+        if ((f0 - f1) * pcg_double(s, inc) + f1 < exp(-0.5 * x * x)) break;
+        // rejected: a fresh attempt, exactly the top of numpy's for(;;)
+        uint64_t r = pcg_next64(s, inc);
+        idx = (int)(r & 0xff);
+        rabs = (r >> 9) & 0x000fffffffffffffULL;
+        x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb->wi[idx];
+        if ((r >> 8) & 1) x = -x;
+        if (rabs < tb->ki[idx]) break;
     }
-    double f1 = tb.fi[idx], f0 = tb.fi[idx - 1];
-    // exp() here only feeds a comparison; a 1-ulp difference from glibc's exp flips
-    // the outcome with probability ~2^-52 per wedge test (documented in DESIGN.md).
-    return (f0 - f1) * pcg_double(s, inc) + f1 < exp(-0.5 * x * x);
+    out.x = x; out.hi = s.hi; out.lo = s.lo;
+    return out;
 }
 
 // One standard normal (Generator.standard_normal), advancing the stream.
 __device__ __forceinline__ double zig_normal(const ZigTables& tb, Pcg64& s, const PcgInc& inc) {
-    for (;;) {
-        uint64_t r = pcg_next64(s, inc);
-        int idx = (int)(r & 0xff);
-        uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
-        // rabs < 2^52: exact int -> double through the 2^52 magic constant (one DADD)
-        double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
-        if ((r >> 8) & 1) x = -x;
-        if (rabs < tb.ki[idx]) return x;
-        if (zig_slow(tb, s, inc, idx, rabs, x)) return x;
-    }
+    uint64_t r = pcg_next64(s, inc);
+    int idx = (int)(r & 0xff);
+    uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
+    // rabs < 2^52: exact int -> double through the 2^52 magic constant (one DADD)
+    double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
+    if ((r >> 8) & 1) x = -x;
+    if (rabs < tb.ki[idx]) return x;
+    ZigSlowRet o = zig_slow(&tb, s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
+    s.hi = o.hi; s.lo = o.lo;
+    return o.x;
 }
 
 // Advance the stream past one normal without forming its value on the fast path
 // (used to find where the label draws start: choice() comes after all normals).
 __device__ __forceinline__ void zig_skip(const ZigTables& tb, Pcg64& s, const PcgInc& inc) {
-    for (;;) {
-        uint64_t r = pcg_next64(s, inc);
-        int idx = (int)(r & 0xff);
-        uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
-        if (rabs < tb.ki[idx]) return;
-        double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
-        if ((r >> 8) & 1) x = -x;
-        if (zig_slow(tb, s, inc, idx, rabs, x)) return;
-    }
+    uint64_t r = pcg_next64(s, inc);
+    int idx = (int)(r & 0xff);
+    uint64_t rabs = (r >> 9) & 0x000fffffffffffffULL;
+    if (rabs < tb.ki[idx]) return;
+    double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
+    if ((r >> 8) & 1) x = -x;
+    ZigSlowRet o = zig_slow(&tb, s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
+    s.hi = o.hi; s.lo = o.lo;
 }
 
 }  // namespace oco

@@ -75,17 +75,39 @@ OCO_API int oco_abi_version(void);
 OCO_API int oco_device_count(int* count);
 
 /* ---- fast_algorithms.simulate_alg (fast_algorithms.py:171-177 -> _simulate_alg_core :88-115),
- * batched over B sequences and A variants.  Outputs (device, [B*A] unless noted, any may be
- * NULL): regret = cum_loss - comp_loss, cum_loss, comp_loss, theta_final [B*A*d],
- * x_trace [B*A*T*d] (the played iterates x_t; d <= 8 only). */
+ * batched over B sequences and A variants; also exact_ftl._simulate_ftrl (exact_ftl.py:230-277)
+ * when `comparator` is given.  comparator: optional [B*d] fixed comparator action per sequence
+ * (exact_ftl.run_ftrl(..., comparator_action=...)); NULL = the reference's FTL action of the
+ * final theta (d <= 8 only).  Outputs ([B*A] unless noted, any may be NULL): regret =
+ * cum_loss - comp_loss, cum_loss, comp_loss, theta_final [B*A*d], x_last [B*A*d] (the action
+ * played at the last round, RunResult.x_last; d <= 8), x_trace [B*A*T*d] (all played x_t; d <= 8). */
 OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
-                       const int* alg_flag, const double* eta0, int A,
+                       const int* alg_flag, const double* eta0, int A, const double* comparator,
                        double* regret, double* cum_loss, double* comp_loss,
-                       double* theta_final, double* x_trace, int comparator_mode, void* stream);
+                       double* theta_final, double* x_last, double* x_trace, int comparator_mode, void* stream);
 OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
-                            const int* alg_flag, const double* eta0, int A,
+                            const int* alg_flag, const double* eta0, int A, const double* comparator,
                             double* regret, double* cum_loss, double* comp_loss,
-                            double* theta_final, double* x_trace, int comparator_mode, int device);
+                            double* theta_final, double* x_last, double* x_trace, int comparator_mode, int device);
+
+/* ---- exact_ftl.compute_prefix_actions + replay_exact_ftl (exact_ftl.py:280-333) for the unit
+ * l2 ball, batched, d <= 8, in the LINEAR REGIME only (every row ||z_t||_2 <= 1, y_t = +-1;
+ * there the SOCP of exact_ftl.py:83-105 has the closed-form minimiser v_k/||v_k||,
+ * v_k = sum_{i<k} y_i z_i, and 0 on ties).  actions [B*(T+1)*d] (may be NULL), cum_loss /
+ * comp_loss / regret [B] (may be NULL), status [B]: 0 = ok, 1 = some row is outside the regime
+ * (results for that sequence are NOT the exact optimum and must be discarded).
+ * PARITY UNPINNED: the reference's arithmetic for this path lives in CVXPY's conic solver. */
+OCO_API int oco_exact_ftl_prefix_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                               double* actions, double* cum_loss, double* comp_loss, double* regret,
+                               int* status, void* stream);
+OCO_API int oco_exact_ftl_prefix_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                                    double* actions, double* cum_loss, double* comp_loss, double* regret,
+                                    int* status, int device);
+
+/* ---- exact_ftl.replay_exact_ftl (exact_ftl.py:306-333) for caller-supplied actions [B*(T+1)*d]:
+ * cum_loss = sum_t 0.5|z_t.actions[t] - y_t|, comp_loss = 0.5 sum_t |z_t.actions[T] - y_t|. d <= 8. */
+OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                                  const double* actions, double* cum_loss, double* comp_loss, double* regret, int device);
 
 /* ---- fast_algorithms.simulate_SMART_like (fast_algorithms.py:184-195 -> :118-164), batched;
  * A <= OCO_MAX_SMART_THRESHOLDS (theta_thresh[a], eta0[a]) pairs per sequence, d <= 8.

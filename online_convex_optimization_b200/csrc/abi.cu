@@ -111,12 +111,13 @@ OCO_API int oco_device_count(int* count) {
 
 // ---------------------------------------------------------------------------------- simulate
 OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
-                       const int* alg_flag, const double* eta0, int A,
+                       const int* alg_flag, const double* eta0, int A, const double* comparator,
                        double* regret, double* cum_loss, double* comp_loss,
-                       double* theta_final, double* x_trace, int comparator_mode, void* stream) {
+                       double* theta_final, double* x_last, double* x_trace, int comparator_mode, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     if (d > 256) return fail(OCO_ERR_VALUE, "d <= 256 supported (got %d)", d);
-    if (x_trace && d > kMaxSmallD) return fail(OCO_ERR_VALUE, "x_trace is available for d <= %d only", kMaxSmallD);
+    if ((x_trace || x_last || comparator) && d > kMaxSmallD)
+        return fail(OCO_ERR_VALUE, "x_trace / x_last / comparator are available for d <= %d only", kMaxSmallD);
     if (comparator_mode != OCO_COMPARATOR_TWO_PASS && comparator_mode != OCO_COMPARATOR_LINEAR)
         return fail(OCO_ERR_VALUE, "unknown comparator_mode %d", comparator_mode);
     Variants v; Etas e;
@@ -127,16 +128,17 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64
     CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
     CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
     if (d <= kMaxSmallD)
-        CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, x_trace, st));
+        CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), comparator, regret, cum_loss, comp_loss,
+                             theta_final, x_last, x_trace, st));
     else
         CU(launch_sim_wide(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, comparator_mode, st));
     return OCO_OK;
 }
 
 OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
-                            const int* alg_flag, const double* eta0, int A,
+                            const int* alg_flag, const double* eta0, int A, const double* comparator,
                             double* regret, double* cum_loss, double* comp_loss,
-                            double* theta_final, double* x_trace, int comparator_mode, int device) {
+                            double* theta_final, double* x_last, double* x_trace, int comparator_mode, int device) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     if (B == 0) return OCO_OK;
@@ -147,12 +149,14 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
     // chunk so that one buffer set stays <= ~256 MiB; two sets are in flight
     int64_t chunk = (int64_t)std::max<size_t>(1, (256u << 20) / std::max<size_t>(1, seq_bytes + out_per_seq));
     chunk = std::min<int64_t>(chunk, B);
-    DevBuf zd[2], yd[2], rd[2], cd[2], pd[2], td[2], xd[2];
+    DevBuf zd[2], yd[2], rd[2], cd[2], pd[2], td[2], xd[2], ld[2], qd[2];
     for (int i = 0; i < 2; ++i) {
         cudaStream_t s = sp.s[i];
         CU(zd[i].alloc((size_t)chunk * T * d * es, s)); CU(yd[i].alloc((size_t)chunk * T * es, s));
         CU(rd[i].alloc((size_t)chunk * A * 8, s)); CU(cd[i].alloc((size_t)chunk * A * 8, s)); CU(pd[i].alloc((size_t)chunk * A * 8, s));
         if (theta_final) CU(td[i].alloc((size_t)chunk * A * d * 8, s));
+        if (x_last) CU(ld[i].alloc((size_t)chunk * A * d * 8, s));
+        if (comparator) CU(qd[i].alloc((size_t)chunk * d * 8, s));
         if (x_trace) CU(xd[i].alloc((size_t)chunk * A * T * d * 8, s));
     }
     int it = 0;
@@ -161,10 +165,13 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
         const int64_t nb = std::min<int64_t>(chunk, B - b0);
         CU(cudaMemcpyAsync(zd[i].p, (const char*)z + (size_t)b0 * T * d * es, (size_t)nb * T * d * es, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(yd[i].p, (const char*)y + (size_t)b0 * T * es, (size_t)nb * T * es, cudaMemcpyHostToDevice, s));
+        if (comparator) CU(cudaMemcpyAsync(qd[i].p, comparator + b0 * d, (size_t)nb * d * 8, cudaMemcpyHostToDevice, s));
         if (int rc = oco_simulate_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, alg_flag, eta0, A,
+                                        comparator ? qd[i].as<double>() : nullptr,
                                         rd[i].as<double>(), cd[i].as<double>(), pd[i].as<double>(),
-                                        theta_final ? td[i].as<double>() : nullptr, x_trace ? xd[i].as<double>() : nullptr,
-                                        comparator_mode, s)) return rc;
+                                        theta_final ? td[i].as<double>() : nullptr, x_last ? ld[i].as<double>() : nullptr,
+                                        x_trace ? xd[i].as<double>() : nullptr, comparator_mode, s)) return rc;
+        if (x_last) CU(cudaMemcpyAsync(x_last + b0 * A * d, ld[i].p, (size_t)nb * A * d * 8, cudaMemcpyDeviceToHost, s));
         if (regret) CU(cudaMemcpyAsync(regret + b0 * A, rd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
         if (cum_loss) CU(cudaMemcpyAsync(cum_loss + b0 * A, cd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
         if (comp_loss) CU(cudaMemcpyAsync(comp_loss + b0 * A, pd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
@@ -173,6 +180,92 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
     }
     CU(cudaStreamSynchronize(sp.s[0])); CU(cudaStreamSynchronize(sp.s[1]));
     return OCO_OK;
+}
+
+// ---------------------------------------------------------------------------------- exact FTL (linear regime)
+OCO_API int oco_exact_ftl_prefix_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                               double* actions, double* cum_loss, double* comp_loss, double* regret,
+                               int* status, void* stream) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
+    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "exact FTL: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (B > 0 && !status) return fail(OCO_ERR_VALUE, "status must not be NULL");
+    if (B == 0) return OCO_OK;
+    CU(launch_exact_ftl_linear(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, (cudaStream_t)stream));
+    return OCO_OK;
+}
+
+OCO_API int oco_exact_ftl_prefix_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                                    double* actions, double* cum_loss, double* comp_loss, double* regret,
+                                    int* status, int device) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
+    if (B > 0 && !status) return fail(OCO_ERR_VALUE, "status must not be NULL");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0) return OCO_OK;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t es = elem_size(in_dtype);
+    int rc = OCO_OK;
+    {
+        DevBuf zd, yd, ad, cd, pd, rd, sd;
+        bool ok = zd.alloc((size_t)B * T * d * es, st) == cudaSuccess && yd.alloc((size_t)B * T * es, st) == cudaSuccess &&
+                  cd.alloc((size_t)B * 8, st) == cudaSuccess && pd.alloc((size_t)B * 8, st) == cudaSuccess &&
+                  rd.alloc((size_t)B * 8, st) == cudaSuccess && sd.alloc((size_t)B * 4, st) == cudaSuccess;
+        if (actions) ok = ok && ad.alloc((size_t)B * (T + 1) * d * 8, st) == cudaSuccess;
+        if (!ok) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        if (!rc && (cudaMemcpyAsync(zd.p, z, (size_t)B * T * d * es, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                    cudaMemcpyAsync(yd.p, y, (size_t)B * T * es, cudaMemcpyHostToDevice, st) != cudaSuccess))
+            rc = fail(OCO_ERR_RUNTIME, "host-to-device copy failed");
+        if (!rc) rc = oco_exact_ftl_prefix_batch(zd.p, yd.p, in_dtype, B, T, d, ad.as<double>(), cd.as<double>(), pd.as<double>(),
+                                                 rd.as<double>(), sd.as<int>(), st);
+        if (!rc) {
+            bool c = cudaMemcpyAsync(status, sd.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (actions) c = c && cudaMemcpyAsync(actions, ad.p, (size_t)B * (T + 1) * d * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (cum_loss) c = c && cudaMemcpyAsync(cum_loss, cd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (comp_loss) c = c && cudaMemcpyAsync(comp_loss, pd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (regret) c = c && cudaMemcpyAsync(regret, rd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (!c) rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+        }
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "exact FTL failed: %s", cudaGetErrorString(es_));
+    return rc;
+}
+
+OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+                                  const double* actions, double* cum_loss, double* comp_loss, double* regret, int device) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
+    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "replay: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (B > 0 && !actions) return fail(OCO_ERR_VALUE, "actions must not be NULL");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0) return OCO_OK;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t es = elem_size(in_dtype);
+    int rc = OCO_OK;
+    {
+        DevBuf zd, yd, ad, cd, pd, rd;
+        const size_t na = (size_t)B * (T + 1) * d * 8;
+        bool ok = zd.alloc((size_t)B * T * d * es, st) == cudaSuccess && yd.alloc((size_t)B * T * es, st) == cudaSuccess &&
+                  ad.alloc(na, st) == cudaSuccess && cd.alloc((size_t)B * 8, st) == cudaSuccess &&
+                  pd.alloc((size_t)B * 8, st) == cudaSuccess && rd.alloc((size_t)B * 8, st) == cudaSuccess;
+        if (!ok) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        if (!rc && ((T > 0 && (cudaMemcpyAsync(zd.p, z, (size_t)B * T * d * es, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                               cudaMemcpyAsync(yd.p, y, (size_t)B * T * es, cudaMemcpyHostToDevice, st) != cudaSuccess)) ||
+                    cudaMemcpyAsync(ad.p, actions, na, cudaMemcpyHostToDevice, st) != cudaSuccess))
+            rc = fail(OCO_ERR_RUNTIME, "host-to-device copy failed");
+        if (!rc && launch_replay_actions(zd.p, yd.p, in_dtype == OCO_F32, B, T, d, ad.as<double>(), cd.as<double>(), pd.as<double>(),
+                                         rd.as<double>(), st) != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "replay launch failed");
+        if (!rc) {
+            bool c = true;
+            if (cum_loss) c = c && cudaMemcpyAsync(cum_loss, cd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (comp_loss) c = c && cudaMemcpyAsync(comp_loss, pd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (regret) c = c && cudaMemcpyAsync(regret, rd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (!c) rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+        }
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "replay failed: %s", cudaGetErrorString(es_));
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------- SMART

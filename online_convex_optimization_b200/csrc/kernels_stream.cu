@@ -23,7 +23,8 @@ struct StreamArgs {
     const void* z; const void* y;
     int64_t B, T;
     const double* tab;
-    double* regret; double* cum; double* comp; double* theta_final; double* x_trace;
+    const double* comparator;    // optional [B][D]: fixed comparator action (exact_ftl.py:255-271) instead of FTL(theta_T)
+    double* regret; double* cum; double* comp; double* theta_final; double* x_last; double* x_trace;
     Variants v;
 };
 
@@ -58,13 +59,26 @@ __global__ void __launch_bounds__(kStreamBlock) sim_stream_kernel(const StreamAr
 #pragma unroll
                     for (int j = 0; j < D; ++j) xo[j] = x[j];
                 }
+                if (p.x_last && t == p.T - 1) {
+                    double* xo = p.x_last + (b * A + v0 + v) * D;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xo[j] = x[j];
+                }
                 play_and_update<D>(s[v], x, z, hz, y);
             }
         }
     }
     double act[AV][D], comp[AV];
 #pragma unroll
-    for (int v = 0; v < AV; ++v) { action_ftl<D>(s[v].th, act[v]); comp[v] = 0.0; }
+    for (int v = 0; v < AV; ++v) {
+        if (p.comparator) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) act[v][j] = p.comparator[b * D + j];
+        } else {
+            action_ftl<D>(s[v].th, act[v]);
+        }
+        comp[v] = 0.0;
+    }
     for (int64_t t = 0; t < p.T; ++t) {
         double z[D];
 #pragma unroll
@@ -114,14 +128,160 @@ static cudaError_t launch_stream_t(const StreamArgs& a, int d, cudaStream_t st) 
 }
 
 cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
-                              const Variants& v, const double* scale_tab,
-                              double* regret, double* cum, double* comp, double* theta_final, double* x_trace,
-                              cudaStream_t st) {
+                              const Variants& v, const double* scale_tab, const double* comparator,
+                              double* regret, double* cum, double* comp, double* theta_final, double* x_last,
+                              double* x_trace, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     StreamArgs a;
-    a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab;
-    a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_trace = x_trace; a.v = v;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.comparator = comparator;
+    a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_last = x_last; a.x_trace = x_trace; a.v = v;
     return in_f32 ? launch_stream_t<float>(a, d, st) : launch_stream_t<double>(a, d, st);
+}
+
+// ------------------------------------------------------------------ exact FTL, linear regime
+// exact_ftl.py:83-105 poses min_{||x||_2 <= 1} 0.5 * sum_{i<k} |z_i.x - y_i| for every prefix k
+// (compute_prefix_actions, exact_ftl.py:280-303).  When every row has ||z_i||_2 <= 1 and
+// y_i in {-1,+1} -- true for every generator the reference's drivers use -- |z_i.x| <= 1 on the
+// ball, the objective is the LINEAR function 0.5 * (k - x.v_k), v_k = sum_{i<k} y_i z_i, and the
+// minimiser is v_k/||v_k|| (the centre 0 when v_k = 0, the tie-break an interior-point solver
+// returns and the published label-flip regret T/4 implies).  One thread per
+// sequence scans the prefix sums, writes actions[b][k][:], replays the played losses
+// (replay_exact_ftl, exact_ftl.py:306-333) and flags sequences outside the regime (status = 1)
+// so that the caller can refuse them instead of returning a wrong optimum.
+struct ExactArgs {
+    const void* z; const void* y; int64_t B, T;
+    double* actions; double* cum; double* comp; double* regret; int* status;
+};
+
+template <int D, typename TIN>
+__global__ void __launch_bounds__(kStreamBlock) exact_ftl_linear_kernel(const ExactArgs p) {
+    const int64_t b = (int64_t)blockIdx.x * kStreamBlock + threadIdx.x;
+    if (b >= p.B) return;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * D;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
+    double* act = p.actions ? p.actions + b * (p.T + 1) * D : nullptr;
+    double v[D], x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { v[j] = 0.0; x[j] = 0.0; }
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) act[j] = 0.0;
+    }
+    double cum = 0.0; int bad = 0;
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = (double)zb[t * D + j];
+        const double y = (double)yb[t];
+        cum = cum + nhinge(dot_seq<D>(z, x), y);             // x = actions[t], the FTL play at round t
+        double n2 = z[0] * z[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) n2 = n2 + z[j] * z[j];
+        if (!(n2 <= 1.0 + 1e-9) || !(y == 1.0 || y == -1.0)) bad = 1;
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = v[j] + y * z[j];
+        double vn2 = v[0] * v[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) vn2 = vn2 + v[j] * v[j];
+        const double inv = vn2 == 0.0 ? 0.0 : 1.0 / sqrt(vn2);
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = vn2 == 0.0 ? 0.0 : inv * v[j];
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) act[(t + 1) * D + j] = x[j];
+        }
+    }
+    double comp = 0.0;                                         // comparator actions[T] (exact_ftl.py:328-330)
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = (double)zb[t * D + j];
+        const double r = dot_seq<D>(z, x) - (double)yb[t];
+        comp = comp + (r < 0.0 ? -r : r);
+    }
+    comp = 0.5 * comp;
+    if (p.cum) p.cum[b] = cum;
+    if (p.comp) p.comp[b] = comp;
+    if (p.regret) p.regret[b] = cum - comp;
+    if (p.status) p.status[b] = bad;
+}
+
+// replay_exact_ftl (exact_ftl.py:306-333) for caller-supplied actions[B][T+1][D]
+template <int D, typename TIN>
+__global__ void __launch_bounds__(kStreamBlock) replay_actions_kernel(const ExactArgs p) {
+    const int64_t b = (int64_t)blockIdx.x * kStreamBlock + threadIdx.x;
+    if (b >= p.B) return;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * D;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
+    const double* __restrict__ act = p.actions + b * (p.T + 1) * D;
+    double cum = 0.0, comp = 0.0, xT[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) xT[j] = act[p.T * D + j];
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[D], x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) { z[j] = (double)zb[t * D + j]; x[j] = act[t * D + j]; }
+        const double y = (double)yb[t];
+        cum = cum + nhinge(dot_seq<D>(z, x), y);
+        const double r = dot_seq<D>(z, xT) - y;
+        comp = comp + (r < 0.0 ? -r : r);
+    }
+    comp = 0.5 * comp;
+    if (p.cum) p.cum[b] = cum;
+    if (p.comp) p.comp[b] = comp;
+    if (p.regret) p.regret[b] = cum - comp;
+}
+
+template <typename TIN>
+static cudaError_t launch_replay_t(const ExactArgs& a, int d, cudaStream_t st) {
+    const unsigned gx = (unsigned)((a.B + kStreamBlock - 1) / kStreamBlock);
+    switch (d) {
+    case 1: replay_actions_kernel<1, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 2: replay_actions_kernel<2, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 3: replay_actions_kernel<3, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 4: replay_actions_kernel<4, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 5: replay_actions_kernel<5, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 6: replay_actions_kernel<6, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 7: replay_actions_kernel<7, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 8: replay_actions_kernel<8, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                  const double* actions, double* cum, double* comp, double* regret, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    ExactArgs a;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.actions = const_cast<double*>(actions); a.cum = cum; a.comp = comp; a.regret = regret;
+    a.status = nullptr;
+    return in_f32 ? launch_replay_t<float>(a, d, st) : launch_replay_t<double>(a, d, st);
+}
+
+template <typename TIN>
+static cudaError_t launch_exact_t(const ExactArgs& a, int d, cudaStream_t st) {
+    const unsigned gx = (unsigned)((a.B + kStreamBlock - 1) / kStreamBlock);
+    switch (d) {
+    case 1: exact_ftl_linear_kernel<1, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 2: exact_ftl_linear_kernel<2, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 3: exact_ftl_linear_kernel<3, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 4: exact_ftl_linear_kernel<4, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 5: exact_ftl_linear_kernel<5, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 6: exact_ftl_linear_kernel<6, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 7: exact_ftl_linear_kernel<7, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    case 8: exact_ftl_linear_kernel<8, TIN><<<gx, kStreamBlock, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exact_ftl_linear(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                    double* actions, double* cum, double* comp, double* regret, int* status,
+                                    cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    ExactArgs a;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.actions = actions; a.cum = cum; a.comp = comp; a.regret = regret; a.status = status;
+    return in_f32 ? launch_exact_t<float>(a, d, st) : launch_exact_t<double>(a, d, st);
 }
 
 }  // namespace oco

@@ -44,13 +44,19 @@ cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint6
 
 // Streamed simulators on device-resident sequences (z[B][T][d], y[B][T]; f32 or f64).
 cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
-                              const Variants& v, const double* scale_tab,
-                              double* regret, double* cum, double* comp, double* theta_final, double* x_trace,
-                              cudaStream_t st);
+                              const Variants& v, const double* scale_tab, const double* comparator,
+                              double* regret, double* cum, double* comp, double* theta_final, double* x_last,
+                              double* x_trace, cudaStream_t st);
+// exact FTL prefix actions + replay in the linear regime (||z||<=1, y=+-1), d <= 8
+cudaError_t launch_exact_ftl_linear(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                    double* actions, double* cum, double* comp, double* regret, int* status,
+                                    cudaStream_t st);
 cudaError_t launch_sim_wide(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                             const Variants& v, const double* scale_tab,
                             double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
                             cudaStream_t st);
+cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                  const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
 // SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).
 cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                          const double* thresh_dev, const double* scale_tab, int A,

@@ -65,9 +65,10 @@ def _keys(keys, B):
 
 # ----------------------------------------------------------------------------- host API
 def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = False,
-                   comparator: str = "two_pass", device: int = 0):
+                   comparator: str = "two_pass", comparator_action=None, device: int = 0):
     """Batched fast_algorithms.simulate_alg: z (B,T,d), y (B,T) -> regret (B,A).
-    full=True returns a dict with cum_loss, comp_loss, theta (B,A,d) [and x_trace (B,A,T,d)]."""
+    full=True returns a dict with cum_loss, comp_loss, theta (B,A,d), x_last (B,A,d; d <= 8)
+    [and x_trace (B,A,T,d)].  comparator_action (B,d): fixed comparator (exact_ftl.run_ftrl)."""
     z, y, dt = _prep_zy(z, y)
     B, T, d = z.shape
     af, et = _variants(alg_flags, eta0s)
@@ -76,13 +77,44 @@ def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = 
     cum = np.empty((B, A)) if full else None
     comp = np.empty((B, A)) if full else None
     th = np.empty((B, A, d)) if full else None
+    xl = np.zeros((B, A, d)) if (full and d <= 8) else None
     xt = np.empty((B, A, T, d)) if trace else None
+    ca = None
+    if comparator_action is not None:
+        ca = np.ascontiguousarray(comparator_action, dtype=np.float64).reshape(-1, d)
+        if ca.shape != (B, d):
+            raise ValueError(f"comparator_action must have shape ({B}, {d})")
     mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
-    _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(af), _vp(et), A,
-                                                   _vp(reg), _vp(cum), _vp(comp), _vp(th), _vp(xt), mode, device))
+    _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(af), _vp(et), A, _vp(ca),
+                                                   _vp(reg), _vp(cum), _vp(comp), _vp(th), _vp(xl), _vp(xt), mode, device))
     if not full and not trace:
         return reg
-    return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th, "x_trace": xt}
+    return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th, "x_last": xl, "x_trace": xt}
+
+
+def exact_ftl_prefix_batch(z, y, *, want_actions: bool = True, device: int = 0):
+    """Batched exact-FTL prefix actions + replay (unit l2 ball, linear regime; see oco_b200.h).
+    Returns dict(actions (B,T+1,d) | None, cum_loss, comp_loss, regret (B,), status (B,) int32)."""
+    z, y, dt = _prep_zy(z, y)
+    B, T, d = z.shape
+    act = np.empty((B, T + 1, d)) if want_actions else None
+    cum, comp, reg = np.empty(B), np.empty(B), np.empty(B)
+    status = np.zeros(B, dtype=np.int32)
+    _lib.check(_lib.load().oco_exact_ftl_prefix_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(act), _vp(cum), _vp(comp),
+                                                           _vp(reg), _vp(status), device))
+    return {"actions": act, "cum_loss": cum, "comp_loss": comp, "regret": reg, "status": status}
+
+
+def replay_actions(z, y, actions, *, device: int = 0):
+    """Batched exact_ftl.replay_exact_ftl: z (B,T,d), y (B,T), actions (B,T+1,d) -> dict of (B,) arrays."""
+    z, y, dt = _prep_zy(z, y)
+    B, T, d = z.shape
+    act = np.ascontiguousarray(actions, dtype=np.float64)
+    if act.shape != (B, T + 1, d):
+        raise ValueError("actions must have shape (B, T+1, d)")
+    cum, comp, reg = np.empty(B), np.empty(B), np.empty(B)
+    _lib.check(_lib.load().oco_replay_actions_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(act), _vp(cum), _vp(comp), _vp(reg), device))
+    return {"cum_loss": cum, "comp_loss": comp, "regret": reg}
 
 
 def smart_batch(z, y, theta_threshs, eta0s, *, device: int = 0):
@@ -189,8 +221,8 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
     mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
-                                                  B, T, d, _vp(af), _vp(et), A, _dptr(reg), _dptr(cum), _dptr(comp),
-                                                  _dptr(th), None, mode, _stream_ptr(torch)))
+                                                  B, T, d, _vp(af), _vp(et), A, None, _dptr(reg), _dptr(cum), _dptr(comp),
+                                                  _dptr(th), None, None, mode, _stream_ptr(torch)))
     if not full:
         return reg
     return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th}

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kStreamBlock) exact_ftl_linear_kernel(const Ex
         double n2 = z[0] * z[0];
 #pragma unroll
         for (int j = 1; j < D; ++j) n2 = n2 + z[j] * z[j];
-        if (!(n2 <= 1.0 + 1e-9) || !(y == 1.0 || y == -1.0)) bad = 1;
+        if (!(n2 <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) bad = 1;
 #pragma unroll
         for (int j = 0; j < D; ++j) v[j] = v[j] + y * z[j];
         double vn2 = v[0] * v[0];

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kWideWarps * 32) sim_wide_kernel(const WideArg
         for (int k = 0; k < K; ++k) th[k] = th[k] + g * z[k];
         if (p.comparator_mode == 1) {
             zz = warp_sum(zz);
-            if (!(zz <= 1.0 + 1e-9) || !(y == 1.0 || y == -1.0)) linear_ok = false;
+            if (!(zz <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) linear_ok = false;
 #pragma unroll
             for (int k = 0; k < K; ++k) vy[k] = vy[k] + y * z[k];
         }
@@ -333,7 +333,7 @@ cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, in
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double m, double c) {
     double a[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-6 * (threadIdx.x + k);
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a[k] = a[k] * m; a[k] = a[k] + c; }

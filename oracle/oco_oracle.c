@@ -549,7 +549,7 @@ API int oracle_exact_ftl_l2_prefix(const double *z, const double *y, int64_t T, 
     for (int64_t t = 0; t < T; ++t) {
         const double *zt = z + t * d;
         double n2 = 0.0; for (int j = 0; j < d; ++j) n2 += zt[j] * zt[j];
-        if (!(n2 <= 1.0 + 1e-9) || !(y[t] == 1.0 || y[t] == -1.0)) return 1;
+        if (!(n2 <= 1.0 + 1e-6) || !(y[t] == 1.0 || y[t] == -1.0)) return 1;
         for (int j = 0; j < d; ++j) v[j] += y[t] * zt[j];
         double vn2 = 0.0; for (int j = 0; j < d; ++j) vn2 += v[j] * v[j];
         double *a = actions + (t + 1) * d;

@@ -373,14 +373,16 @@ OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const 
         if (stats) CU(cudaMemsetAsync(stats, 0, sizeof(double) * 4 * A, st));
         return OCO_OK;
     }
+    if (T > 0x7fffffff) return fail(OCO_ERR_VALUE, "T must be < 2^31");
     DevBuf tab, kb, part;
-    CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
-    CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
+    SweepPlan plan; make_sweep_plan(v, e, &plan);
+    CU(tab.alloc(sizeof(double) * (size_t)sweep_table_elems(plan, T), st));
+    CU(launch_sweep_table(tab.as<double>(), plan, T, st));
     const uint64_t* kd = nullptr;
     if (int rc = upload_keys(keys, B, kb, st, &kd)) return rc;
     const int nblocks = sweep_gpath_blocks(B);
     if (stats) CU(part.alloc(sizeof(double) * 3 * (size_t)nblocks * A, st));
-    CU(launch_sweep(family, key_a, key_c0, kd, T, B, d, p_flip, v, tab.as<double>(), regret, cum_loss, comp_loss,
+    CU(launch_sweep(family, key_a, key_c0, kd, T, B, d, p_flip, plan, tab.as<double>(), regret, cum_loss, comp_loss,
                     stats ? part.as<double>() : nullptr, st));
     if (stats) CU(launch_stats_finalize(part.as<double>(), nblocks, A, B, stats, st));
     return OCO_OK;

@@ -9,128 +9,9 @@
 //  fill_kernel<Stream, D, TOUT>  write the sequences to HBM (z[B][T][d], y[B][T]) for the
 //      streamed kernels (BASELINE config 4) and for callers that want the arrays.
 //  stats_finalize_kernel        fixed-order reduction of the per-block (max, sum, sumsq).
-#include "oco_device.cuh"
-#include "oco_internal.h"
-#include "streams.cuh"
+#include "sweep_impl.cuh"
 
 namespace oco {
-
-constexpr int kSweepBlock = 128;
-
-struct SweepArgs {
-    uint64_t key_a;          // first entropy word (base_seed / run_seed) when keys == nullptr
-    uint64_t key_c0;         // third entropy word of sequence 0 (run_lo); sequence b uses key_c0 + b
-    const uint64_t* keys;    // optional device [B][2] explicit (a, c) pairs
-    int64_t T, B;
-    int family;
-    double p_flip;
-    const double* tab;       // [T][A] FTRL scales
-    double* regret; double* cum; double* comp;   // [B][A] or nullptr
-    double* partials;        // [gridDim.x][A][3] or nullptr
-    Variants v;
-};
-
-template <class Stream, int D, int AV>
-__global__ void __launch_bounds__(kSweepBlock) sweep_kernel(const SweepArgs p) {
-    __shared__ ZigTables tb;
-    __shared__ double red[kSweepBlock / 32][3];
-    zig_tables_load(tb);
-
-    const int64_t b = (int64_t)blockIdx.x * kSweepBlock + threadIdx.x;
-    const bool active = b < p.B;
-    const int A = p.v.A;
-    const int v0 = blockIdx.y * AV;
-    const int nv = min(AV, A - v0);
-    typedef typename Stream::elem_t E;
-
-    double regret[AV];
-#pragma unroll
-    for (int v = 0; v < AV; ++v) regret[v] = 0.0;
-
-    if (active) {
-        Stream st;
-        const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
-        const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
-        st.init(tb, ka, p.T, kc, p.p_flip, p.family);
-
-        TrajState<D> s[AV];
-#pragma unroll
-        for (int v = 0; v < AV; ++v) traj_init<D>(s[v]);
-
-        // ---- pass 1: play (fast_algorithms.py:99-111)
-        for (int64_t t = 0; t < p.T; ++t) {
-            E ze[D]; E ye;
-            st.next(tb, t, ze, ye);
-            double z[D], hz[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) { z[j] = (double)ze[j]; hz[j] = 0.5 * z[j]; }
-            const double y = (double)ye;
-            const double* trow = p.tab + t * A + v0;
-#pragma unroll
-            for (int v = 0; v < AV; ++v) {
-                if (v < nv) {
-                    double x[D];
-                    if (p.v.alg_flag[v0 + v] == 0) action_ftrl<D>(s[v].th, __ldg(trow + v), x);
-                    else action_ftl<D>(s[v].th, x);
-                    play_and_update<D>(s[v], x, z, hz, y);
-                }
-            }
-        }
-        // ---- pass 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114)
-        double act[AV][D], comp[AV];
-#pragma unroll
-        for (int v = 0; v < AV; ++v) { action_ftl<D>(s[v].th, act[v]); comp[v] = 0.0; }
-        st.rewind();
-        for (int64_t t = 0; t < p.T; ++t) {
-            E ze[D]; E ye;
-            st.next(tb, t, ze, ye);
-            double z[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) z[j] = (double)ze[j];
-            const double y = (double)ye;
-#pragma unroll
-            for (int v = 0; v < AV; ++v)
-                if (v < nv) comp[v] = comp[v] + nhinge(dot_seq<D>(z, act[v]), y);
-        }
-#pragma unroll
-        for (int v = 0; v < AV; ++v) {
-            if (v < nv) {
-                regret[v] = s[v].cum - comp[v];
-                const int64_t o = b * A + v0 + v;
-                if (p.regret) p.regret[o] = regret[v];
-                if (p.cum) p.cum[o] = s[v].cum;
-                if (p.comp) p.comp[o] = comp[v];
-            }
-        }
-    }
-
-    // ---- per-block (max, sum, sumsq) of the regrets, fixed order -> deterministic
-    if (p.partials) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int v = 0; v < nv; ++v) {
-            double r = 0.0;
-#pragma unroll
-            for (int k = 0; k < AV; ++k) if (k == v) r = regret[k];
-            double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
-            double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
-                sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
-                sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
-            }
-            if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
-                for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
-                double* o = p.partials + ((int64_t)blockIdx.x * A + v0 + v) * 3;
-                o[0] = m; o[1] = s1; o[2] = s2;
-            }
-            __syncthreads();
-        }
-    }
-}
 
 __global__ void stats_finalize_kernel(const double* __restrict__ partials, int nblocks, int A, int64_t n_runs,
                                       double* __restrict__ stats) {
@@ -161,42 +42,45 @@ cudaError_t launch_ftrl_scale_table(double* tab, const Etas& eta0, int64_t T, in
 
 int sweep_gpath_blocks(int64_t n_runs) { return (int)((n_runs + kSweepBlock - 1) / kSweepBlock); }
 
-template <template <int> class StreamT, int D>
-static cudaError_t launch_sweep_d(const SweepArgs& a, cudaStream_t st) {
-    typedef StreamT<D> Stream;
-    const int A = a.v.A;
-    const unsigned gx = (unsigned)((a.B + kSweepBlock - 1) / kSweepBlock);
-    if (A == 1) {
-        sweep_kernel<Stream, D, 1><<<dim3(gx, 1), kSweepBlock, 0, st>>>(a);
-    } else if (A <= 3) {
-        sweep_kernel<Stream, D, 3><<<dim3(gx, 1), kSweepBlock, 0, st>>>(a);
-    } else {
-        sweep_kernel<Stream, D, 9><<<dim3(gx, (A + 8) / 9), kSweepBlock, 0, st>>>(a);
+
+void make_sweep_plan(const Variants& v, const Etas& e, SweepPlan* pl) {
+    pl->A = v.A; pl->n_ftl = 0; pl->n_ftrl = 0;
+    for (int a = 0; a < kMaxVariants + 8; ++a) { pl->ftrl_col[a] = 0; pl->ftrl_eta[a] = 0.0; }
+    for (int a = 0; a < kMaxVariants; ++a) pl->ftl_col[a] = 0;
+    for (int a = 0; a < v.A; ++a) {
+        if (v.alg_flag[a] == 0) { pl->ftrl_col[pl->n_ftrl] = a; pl->ftrl_eta[pl->n_ftrl] = e.e[a]; ++pl->n_ftrl; }
+        else pl->ftl_col[pl->n_ftl++] = a;
     }
+    pl->nf_tpl = pl->n_ftrl <= 1 ? 1 : (pl->n_ftrl <= 4 ? 4 : 8);
+    pl->groups = pl->n_ftrl == 0 ? 1 : (pl->n_ftrl + pl->nf_tpl - 1) / pl->nf_tpl;
+}
+
+__global__ void sweep_table_kernel(double* __restrict__ tab, const SweepPlan pl, int64_t T) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)pl.groups * pl.nf_tpl * T;
+    if (i >= n) return;
+    const int k = (int)(i % pl.nf_tpl);
+    const int64_t gt = i / pl.nf_tpl;
+    const int64_t t = gt % T; const int g = (int)(gt / T);
+    tab[i] = -(pl.ftrl_eta[g * pl.nf_tpl + k] / sqrt((double)(t + 1)));   // fast_algorithms.py:54
+}
+cudaError_t launch_sweep_table(double* tab, const SweepPlan& plan, int64_t T, cudaStream_t st) {
+    const int64_t n = sweep_table_elems(plan, T);
+    if (n <= 0) return cudaSuccess;
+    sweep_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tab, plan, T);
     return cudaGetLastError();
 }
 
-template <template <int> class StreamT>
-static cudaError_t launch_sweep_s(const SweepArgs& a, int d, cudaStream_t st) {
-    switch (d) {
-    case 1: return launch_sweep_d<StreamT, 1>(a, st);
-    case 2: return launch_sweep_d<StreamT, 2>(a, st);
-    case 3: return launch_sweep_d<StreamT, 3>(a, st);
-    case 4: return launch_sweep_d<StreamT, 4>(a, st);
-    case 5: return launch_sweep_d<StreamT, 5>(a, st);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
 cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
-                         double p_flip, const Variants& v, const double* scale_tab,
+                         double p_flip, const SweepPlan& plan, const double* sweep_tab,
                          double* regret, double* cum, double* comp, double* partials, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
+    if (T > 0x7fffffff) return cudaErrorInvalidValue;
     SweepArgs a;
-    a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = T; a.B = B; a.family = family; a.p_flip = p_flip;
-    a.tab = scale_tab; a.regret = regret; a.cum = cum; a.comp = comp; a.partials = partials; a.v = v;
-    if (family == FAM_GPATH) return launch_sweep_s<GPathStream>(a, d, st);
-    if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_s<IidStream>(a, d, st);
+    a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = (int)T; a.B = B; a.family = family; a.p_flip = p_flip;
+    a.tab = sweep_tab; a.regret = regret; a.cum = cum; a.comp = comp; a.partials = partials; a.plan = plan;
+    if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);
+    if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_iid(a, d, st);
     return cudaErrorInvalidValue;
 }
 

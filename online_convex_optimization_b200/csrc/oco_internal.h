@@ -26,13 +26,31 @@ struct Etas { double e[kMaxVariants]; };
 // tab[t*A + a] = -(eta0[a] / sqrt(max(1, t+1)))
 cudaError_t launch_ftrl_scale_table(double* tab, const Etas& eta0, int64_t T, int A, cudaStream_t st);
 
+// Canonical layout of the variants of one sweep: FTL ignores eta0 (fast_algorithms.py:102-103), so
+// one FTL trajectory serves all FTL columns; FTRL variants are processed nf_tpl at a time.
+struct SweepPlan {
+    int A;                              // output columns
+    int n_ftl, n_ftrl;                  // number of FTL / FTRL columns
+    int nf_tpl;                         // FTRL variants per thread (template NF: 1, 4 or 8)
+    int groups;                         // grid.y = max(1, ceil(n_ftrl / nf_tpl))
+    int ftl_col[kMaxVariants];
+    int ftrl_col[kMaxVariants + 8];     // padded to groups * nf_tpl
+    double ftrl_eta[kMaxVariants + 8];  // padding: 0.0
+};
+void make_sweep_plan(const Variants& v, const Etas& e, SweepPlan* plan);
+inline int64_t sweep_table_elems(const SweepPlan& pl, int64_t T) { return (int64_t)pl.groups * pl.nf_tpl * T; }
+// tab[(g*T + t)*nf_tpl + k] = -(eta[g*nf_tpl + k] / sqrt(max(1, t+1)))
+cudaError_t launch_sweep_table(double* tab, const SweepPlan& plan, int64_t T, cudaStream_t st);
+
 // Fused generate + simulate + compare (no HBM traffic for inputs).  Sequence b has
 // stream key SeedSequence([a, T, c]) with (a, c) = keys[b] when keys != NULL (device
 // [B][2]), else (key_a, key_c0 + b).  regret/cum/comp: device [B*A] or NULL.
 // partials: device [blocks * A * 3] (max, sum, sumsq per block) or NULL.
 cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
-                         double p_flip, const Variants& v, const double* scale_tab,
+                         double p_flip, const SweepPlan& plan, const double* sweep_tab,
                          double* regret, double* cum, double* comp, double* partials, cudaStream_t st);
+cudaError_t launch_sweep_gpath(const struct SweepArgs& a, int d, cudaStream_t st);
+cudaError_t launch_sweep_iid(const struct SweepArgs& a, int d, cudaStream_t st);
 int sweep_gpath_blocks(int64_t n_runs);
 // stats[a*4 + {0,1,2,3}] = max, sum, sumsq, count over all runs (fixed reduction order)
 cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, int64_t n_runs, double* stats, cudaStream_t st);

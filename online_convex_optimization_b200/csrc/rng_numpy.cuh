@@ -211,7 +211,7 @@ __device__ inline double log1p_glibc_fma(double x) {
 // State goes in and out by value so that the fast path keeps it in registers.
 struct ZigSlowRet { double x; uint64_t hi, lo; };
 
-__device__ __noinline__ ZigSlowRet zig_slow(const ZigTables* tb, uint64_t s_hi, uint64_t s_lo,
+static __device__ __noinline__ ZigSlowRet zig_slow(const ZigTables* tb, uint64_t s_hi, uint64_t s_lo,
                                             uint64_t inc_hi, uint64_t inc_lo, int idx, uint64_t rabs, double x) {
     Pcg64 s; s.hi = s_hi; s.lo = s_lo;
     PcgInc inc; inc.hi = inc_hi; inc.lo = inc_lo;

@@ -7,6 +7,7 @@
 // stream), found once per stream by zig_skip(); rewind() restarts both for the
 // comparator pass so that no sequence ever has to be stored.
 #pragma once
+#include "oco_device.cuh"
 #include "rng_numpy.cuh"
 
 namespace oco {
@@ -57,7 +58,7 @@ struct GPathStream {
     __device__ __forceinline__ void next(const ZigTables& tb, int64_t t, double (&z)[D], double& y) {
 #pragma unroll
         for (int j = 0; j < D; ++j) z[j] = zig_normal(tb, zs, inc);
-        double nrm = sqrt(np_pairwise_sumsq<D, double>(z));
+        double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
         double inv = 1.0 / (nrm > 1.0 ? nrm : 1.0);      // z *= 1.0 / np.maximum(norms, 1.0)
 #pragma unroll
         for (int j = 0; j < D; ++j) z[j] = z[j] * inv;

@@ -73,6 +73,20 @@ struct StreamPair {
     ~StreamPair() { for (auto x : s) if (x) cudaStreamDestroy(x); }
 };
 
+// Keep stream-ordered scratch (the sweep kernel's slab can be tens of GB) cached in the device's
+// default memory pool across calls instead of returning it to the driver at every synchronise.
+void retain_pool_memory() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
+}
+
 int upload_keys(const uint64_t* keys, int64_t B, DevBuf& buf, cudaStream_t st, const uint64_t** out) {
     *out = nullptr;
     if (!keys || B <= 0) return OCO_OK;
@@ -374,6 +388,7 @@ OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const 
         return OCO_OK;
     }
     if (T > 0x7fffffff) return fail(OCO_ERR_VALUE, "T must be < 2^31");
+    retain_pool_memory();
     DevBuf tab, kb, part;
     SweepPlan plan; make_sweep_plan(v, e, &plan);
     CU(tab.alloc(sizeof(double) * (size_t)sweep_table_elems(plan, T), st));

@@ -109,13 +109,16 @@ __global__ void __launch_bounds__(128) fill_kernel(const FillArgs p) {
     st.init(tb, ka, p.T, kc, p.p_flip, p.family);
     TOUT* z = (TOUT*)p.z + b * p.T * D;
     TOUT* y = (TOUT*)p.y + b * p.T;
-    for (int64_t t = 0; t < p.T; ++t) {
-        E ze[D]; E ye;
-        st.next(tb, t, ze, ye);
+    const int T = (int)p.T;
+    for (int t = 0; t < T; ++t) {                 // all normals first (numpy order), provisional label parked in y
+        E ze[D]; int ybit;
+        st.row(tb, ze, ybit);
 #pragma unroll
-        for (int j = 0; j < D; ++j) z[t * D + j] = (TOUT)ze[j];
-        y[t] = (TOUT)ye;
+        for (int j = 0; j < D; ++j) z[(int64_t)t * D + j] = (TOUT)ze[j];
+        y[t] = (TOUT)ybit;
     }
+    st.begin_labels();
+    for (int t = 0; t < T; ++t) y[t] = (TOUT)st.label(t, (int)y[t]);
 }
 
 // sequence_generation.py:24-28 (flip) and :36-47 (switching two leaders); any d.

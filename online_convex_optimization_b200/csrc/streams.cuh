@@ -37,40 +37,43 @@ __device__ __forceinline__ F np_pairwise_sumsq(const F (&z)[D]) {
     }
 }
 
+// Stream protocol (one CUDA thread per stream key):
+//   init(...)            seed the generator
+//   row(tb, z, ybit)     next row of normals, clipped as the reference does; ybit = provisional label
+//   begin_labels()       call once after all T rows: numpy draws labels / flip uniforms AFTER the normals
+//   label(t, ybit)       final label of round t (consumes label / flip draws in order t = 0, 1, ...)
+// Rows are produced exactly once per sequence; consumers that need them again (the play pass and
+// the comparator pass of the sweep kernel) keep them in a scratch buffer instead of regenerating.
+
 template <int D>
-struct GPathStream {
+struct GPathStream {                      // fast_algorithms.py:231-239
     typedef double elem_t;
     PcgInc inc;
-    Pcg64 zs, z0, lab0;
+    Pcg64 s;
     LabelCursor lab;
 
     // key = SeedSequence([a, T, c])
     __device__ __forceinline__ void init(const ZigTables& tb, uint64_t a, int64_t T, uint64_t c, double /*p_flip*/, int /*family*/) {
-        pcg_seed3(zs, inc, a, (uint64_t)T, c);
-        z0 = zs;
-        Pcg64 s = zs;
-        for (int64_t i = 0; i < T * D; ++i) zig_skip(tb, s, inc);
-        lab0 = s;
-        rewind();
+        pcg_seed3(s, inc, a, (uint64_t)T, c);
     }
-    __device__ __forceinline__ void rewind() { zs = z0; lab.s = lab0; lab.cur = 0; }
-
-    __device__ __forceinline__ void next(const ZigTables& tb, int64_t t, double (&z)[D], double& y) {
+    __device__ __forceinline__ void row(const ZigTables& tb, double (&z)[D], int& ybit) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) z[j] = zig_normal(tb, zs, inc);
+        for (int j = 0; j < D; ++j) z[j] = zig_normal(tb, s, inc);
         double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
         double inv = 1.0 / (nrm > 1.0 ? nrm : 1.0);      // z *= 1.0 / np.maximum(norms, 1.0)
 #pragma unroll
         for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
-        y = lab.next(t, inc);
+        ybit = 0;
     }
+    __device__ __forceinline__ void begin_labels() { lab.s = s; lab.cur = 0; }
+    __device__ __forceinline__ double label(int t, int /*ybit*/) { return lab.next(t, inc); }   // choice([-1, 1], T)
 };
 
 template <int D>
-struct IidStream {
+struct IidStream {                        // sequence_generation.py:54-90
     typedef float elem_t;
     PcgInc inc;
-    Pcg64 zs, z0, fl, fl0;
+    Pcg64 s;
     float u[D];
     double p_flip;       // < 0: no flips (separable family)
 
@@ -90,20 +93,11 @@ struct IidStream {
             }
         }
         p_flip = (family == 2) ? p : -1.0;
-        pcg_seed3(zs, inc, run_seed, (uint64_t)T, stream_id);
-        z0 = zs; fl0 = zs;
-        if (p_flip >= 0.0) {
-            Pcg64 s = zs;
-            for (int64_t i = 0; i < T * D; ++i) zig_skip(tb, s, inc);
-            fl0 = s;
-        }
-        rewind();
+        pcg_seed3(s, inc, run_seed, (uint64_t)T, stream_id);
     }
-    __device__ __forceinline__ void rewind() { zs = z0; fl = fl0; }
-
-    __device__ __forceinline__ void next(const ZigTables& tb, int64_t /*t*/, float (&z)[D], float& y) {
+    __device__ __forceinline__ void row(const ZigTables& tb, float (&z)[D], int& ybit) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) z[j] = (float)zig_normal(tb, zs, inc);
+        for (int j = 0; j < D; ++j) z[j] = (float)zig_normal(tb, s, inc);
         float nrm = sqrtf(np_pairwise_sumsq<D, float>(z));
         if (!(nrm >= 1.0f)) nrm = 1.0f;                  // np.maximum(norms, 1.0, out=norms)
         float inv = 1.0f / nrm;
@@ -112,8 +106,13 @@ struct IidStream {
         float q = z[0] * u[0];                           // y = sign(z @ u), zeros -> +1
 #pragma unroll
         for (int j = 1; j < D; ++j) q = q + z[j] * u[j];
-        y = (q < 0.0f) ? -1.0f : 1.0f;
-        if (p_flip >= 0.0) { if (pcg_double(fl, inc) < p_flip) y = -y; }
+        ybit = (q < 0.0f) ? 0 : 1;
+    }
+    __device__ __forceinline__ void begin_labels() {}    // the flip uniforms continue the same stream
+    __device__ __forceinline__ float label(int /*t*/, int ybit) {
+        float y = ybit ? 1.0f : -1.0f;
+        if (p_flip >= 0.0) { if (pcg_double(s, inc) < p_flip) y = -y; }   // flips = gen.random(T) < p
+        return y;
     }
 };
 

@@ -1,12 +1,19 @@
 // sweep_impl.cuh -- the fused generate + simulate + compare kernel (the engine's hot kernel).
 //
-//   sweep_kernel<Stream, D, NFTL, NF>: one thread per seeded sequence.  The thread owns the
-//   numpy-compatible RNG cursors of its stream (registers), the state of one optional FTL
-//   trajectory and NF FTRL trajectories (theta and the running sum of |q - y|, registers),
-//   and regenerates the sequence for the comparator pass instead of storing it (the
-//   comparator fast_algorithms.py:113-114 needs the FINAL theta).  HBM traffic: the 8*A-byte
-//   result per sequence plus a broadcast read of the [T][NF] FTRL scale table (L2 resident).
-//   Bound: fp64 pipe / issue slots.
+//   sweep_kernel<Stream, D, NFTL, NF>: one thread per seeded sequence, persistent CTAs.
+//   Phase 0  generate: the thread runs its numpy-compatible stream ONCE (PCG64 + ziggurat + row
+//            clip) and parks the rows in a per-CTA scratch slab in HBM, laid out [t][j][thread]
+//            so that every warp access is one fully coalesced 256-byte (fp64) request.
+//   Phase 1  play: rows stream back (prefetched one step ahead), labels are drawn from the same
+//            stream (numpy draws them after all normals) and packed 32 per word into the slab;
+//            one optional FTL trajectory and NF FTRL trajectories live in registers.
+//   Phase 2  compare: the comparator of fast_algorithms.py:113-114 needs the FINAL theta, so the
+//            rows and label words stream back once more.
+//   Inputs never exist in the reference's [B][T][d] layout and never cross PCIe; the slab is
+//   private to a thread (it re-reads only what it wrote), sized by the number of resident
+//   threads, not by B.  Per trajectory-step the kernel moves (8 + 16)*D/A bytes of HBM/L2 traffic
+//   and issues ~9D+6 algorithmic fp64 ops: it is bound by the fp64 pipe / issue slots
+//   (SURVEY.md 8d), not by HBM.
 //
 //   Bit-exact restatement of fast_algorithms.py:88-115 (see oco_device.cuh); the shortcuts
 //   below are exact identities of IEEE-754 binary64 round-to-nearest arithmetic:
@@ -14,13 +21,16 @@
 //      a power of two commutes with rounding, so 0.5*S == sum(0.5*|q_t - y_t|) bit for bit;
 //    * the gradient step adds (+-)0.5*z by flipping the sign bit of hz = 0.5*z;
 //    * for D == 1, sqrt(fl(x*x)) == |x| whenever x*x neither under- nor overflows (guarded),
-//      which removes the square roots of the d = 1 row clip and FTL action;
+//      which removes the square roots of the d = 1 row clip, projection and FTL action;
 //    * FTL variants ignore eta0 (fast_algorithms.py:102-103): one FTL trajectory serves every
-//      FTL column; the FTRL variants are processed NF at a time (grid.y groups) so that the
-//      per-step code has no data-dependent branch except the rare projection fix-up.
+//      FTL column; the FTRL variants are processed NF at a time (work items = chunk x group);
+//    * the projection x *= 1/||x|| (fast_algorithms.py:61-66) is applied under a warp vote with
+//      the non-projecting lanes multiplying by 1.0/1.0 = 1.0 (exact), so the step has no
+//      divergent branch at all.
 #pragma once
 #include "oco_device.cuh"
 #include "oco_internal.h"
+#include <algorithm>
 #include "streams.cuh"
 
 namespace oco {
@@ -35,8 +45,11 @@ struct SweepArgs {
     int family;
     double p_flip;
     const double* tab;       // [groups][T][NF] FTRL scales -(eta0/sqrt(t+1)), padded with -0.0
+    void* slab_z;            // [gridDim.x][T][D][128] elem_t rows
+    uint32_t* slab_y;        // [gridDim.x][ceil(T/32)][128] packed labels (bit = 1 for y = +1)
     double* regret; double* cum; double* comp;   // [B][A] or nullptr
-    double* partials;        // [gridDim.x][A][3] or nullptr
+    double* partials;        // [chunks][A][3] or nullptr
+    int64_t n_items;         // chunks * groups
     SweepPlan plan;
 };
 
@@ -62,183 +75,229 @@ __device__ __forceinline__ void ftl_action(const double (&th)[D], double (&x)[D]
     for (int j = 0; j < D; ++j) x[j] = (n2 == 0.0) ? 0.0 : sc * th[j];
 }
 
+// x *= 1/||x|| iff !(n2 <= 1) (fast_algorithms.py:61-66), branch-free per lane, skipped per warp
+template <int D>
+__device__ __forceinline__ void project_unit_ball(double (&x)[D], double n2, unsigned mask) {
+    const bool need = !(n2 <= 1.0);
+    if (__any_sync(mask, need)) {
+        const double r = need ? sqrt_of_sumsq<D>(n2, x[0]) : 1.0;
+        const double fac = 1.0 / r;                         // 1.0/1.0 == 1.0: untouched lanes stay bit-identical
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = x[j] * fac;
+    }
+}
+
 template <class Stream, int D, int NFTL, int NF>
 __global__ void __launch_bounds__(kSweepBlock) sweep_kernel(const SweepArgs p) {
     __shared__ ZigTables tb;
     __shared__ double red[kSweepBlock / 32][3];
     zig_tables_load(tb);
-
-    const int64_t b = (int64_t)blockIdx.x * kSweepBlock + threadIdx.x;
-    const bool active = b < p.B;
-    const int A = p.plan.A;
-    const int g = blockIdx.y;
-    const int nf = min(NF, p.plan.n_ftrl - g * NF);          // live FTRL variants of this group (may be <= 0)
-    const bool do_ftl = NFTL > 0 && g == 0 && p.plan.n_ftl > 0;
-    const int T = p.T;
     typedef typename Stream::elem_t E;
+    const int T = p.T, A = p.plan.A, tid = threadIdx.x;
+    const int groups = p.plan.groups;
+    E* __restrict__ zs = reinterpret_cast<E*>(p.slab_z) + (int64_t)blockIdx.x * T * D * kSweepBlock + tid;
+    uint32_t* __restrict__ ys = p.slab_y + (int64_t)blockIdx.x * ((T + 31) / 32) * kSweepBlock + tid;
 
-    double reg_r[NF], reg_l = 0.0;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t chunk = item / groups;
+        const int g = (int)(item - chunk * groups);
+        const int64_t b = chunk * kSweepBlock + tid;
+        const bool active = b < p.B;
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        const int nf = min(NF, p.plan.n_ftrl - g * NF);          // live FTRL variants of this group (may be <= 0)
+        const bool do_ftl = NFTL > 0 && g == 0 && p.plan.n_ftl > 0;
+        double reg_r[NF], reg_l = 0.0;
 #pragma unroll
-    for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
+        for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
 
-    if (active) {
-        Stream st;
-        const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
-        const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
-        st.init(tb, ka, T, kc, p.p_flip, p.family);
-
-        double thr[NF][D], Sr[NF];
-        double thl[D], Sl = 0.0;
+        if (active) {
+            // ---- phase 0: generate the rows once (fast_algorithms.py:231-236 / sequence_generation.py:61-66)
+            Stream st;
+            const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
+            const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
+            st.init(tb, ka, T, kc, p.p_flip, p.family);
+            uint32_t word = 0;
+            for (int t = 0; t < T; ++t) {
+                E ze[D]; int ybit;
+                st.row(tb, ze, ybit);
 #pragma unroll
-        for (int k = 0; k < NF; ++k) {
-            Sr[k] = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) thr[k][j] = 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < D; ++j) thl[j] = 0.0;
-        const double* __restrict__ trow = p.tab + (int64_t)g * T * NF;
-
-        // ---- pass 1: play (fast_algorithms.py:99-111)
-        for (int t = 0; t < T; ++t) {
-            E ze[D]; E ye;
-            st.next(tb, t, ze, ye);
-            double z[D], hz[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) { z[j] = (double)ze[j]; hz[j] = 0.5 * z[j]; }
-            const double y = (double)ye;
-
-            if (NFTL > 0 && do_ftl) {
-                double x[D];
-                ftl_action<D>(thl, x);
-                const double df = dot_seq<D>(z, x) - y;
-                Sl = Sl + fabs(df);
-                grad_step<D>(thl, hz, df);
+                for (int j = 0; j < D; ++j) zs[(int64_t)(t * D + j) * kSweepBlock] = ze[j];
+                word |= (uint32_t)ybit << (t & 31);
+                if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = word; word = 0; }
             }
+            st.begin_labels();
 
-            double sc[NF];
-            if constexpr (NF % 2 == 0) {
+            double thr[NF][D], Sr[NF];
+            double thl[D], Sl = 0.0;
 #pragma unroll
-                for (int k = 0; k < NF; k += 2) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(trow + (int64_t)t * NF + k));
-                    sc[k] = v.x; sc[k + 1] = v.y;
+            for (int k = 0; k < NF; ++k) {
+                Sr[k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) thr[k][j] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) thl[j] = 0.0;
+            const double* __restrict__ trow = p.tab + (int64_t)g * T * NF;
+
+            // ---- phase 1: play (fast_algorithms.py:99-111); rows prefetched one step ahead
+            E zn[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) zn[j] = T > 0 ? zs[(int64_t)j * kSweepBlock] : (E)0;
+            uint32_t prov = 0;
+            for (int t = 0; t < T; ++t) {
+                double z[D], hz[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) { z[j] = (double)zn[j]; hz[j] = 0.5 * z[j]; }
+                if (t + 1 < T) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) zn[j] = zs[(int64_t)((t + 1) * D + j) * kSweepBlock];
                 }
-            } else {
+                if ((t & 31) == 0) { prov = ys[(int64_t)(t >> 5) * kSweepBlock]; word = 0; }
+                const double y = (double)st.label(t, (int)((prov >> (t & 31)) & 1u));
+                word |= (y > 0.0 ? 1u : 0u) << (t & 31);
+                if ((t & 31) == 31 || t == T - 1) ys[(int64_t)(t >> 5) * kSweepBlock] = word;
+
+                if (NFTL > 0 && do_ftl) {
+                    double x[D];
+                    ftl_action<D>(thl, x);
+                    const double df = dot_seq<D>(z, x) - y;
+                    Sl = Sl + fabs(df);
+                    grad_step<D>(thl, hz, df);
+                }
+
+                double sc[NF];
+                if constexpr (NF % 2 == 0) {
 #pragma unroll
-                for (int k = 0; k < NF; ++k) sc[k] = __ldg(trow + (int64_t)t * NF + k);
-            }
-            double x[NF][D], n2[NF];
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < NF; ++k) {                   // fast_algorithms.py:52-60
-#pragma unroll
-                for (int j = 0; j < D; ++j) x[k][j] = sc[k] * thr[k][j];
-                n2[k] = x[k][0] * x[k][0];
-#pragma unroll
-                for (int j = 1; j < D; ++j) n2[k] = n2[k] + x[k][j] * x[k][j];
-                any = any || !(n2[k] <= 1.0);
-            }
-            if (any) {                                        // projection onto the unit ball (:61-66), rare on random labels
-#pragma unroll
-                for (int k = 0; k < NF; ++k) {
-                    if (!(n2[k] <= 1.0)) {
-                        const double fac = 1.0 / sqrt_of_sumsq<D>(n2[k], x[k][0]);
-#pragma unroll
-                        for (int j = 0; j < D; ++j) x[k][j] = x[k][j] * fac;
+                    for (int k = 0; k < NF; k += 2) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(trow + (int64_t)t * NF + k));
+                        sc[k] = v.x; sc[k + 1] = v.y;
                     }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) sc[k] = __ldg(trow + (int64_t)t * NF + k);
+                }
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {                   // fast_algorithms.py:52-66, 105-111
+                    double x[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) x[j] = sc[k] * thr[k][j];
+                    double n2 = x[0] * x[0];
+#pragma unroll
+                    for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                    project_unit_ball<D>(x, n2, mask);
+                    const double df = dot_seq<D>(z, x) - y;
+                    Sr[k] = Sr[k] + fabs(df);
+                    grad_step<D>(thr[k], hz, df);
+                }
+            }
+
+            // ---- phase 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114, 69-76)
+            double ar[NF][D], al[D], Cr[NF], Cl = 0.0;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) { ftl_action<D>(thr[k], ar[k]); Cr[k] = 0.0; }
+            ftl_action<D>(thl, al);
+#pragma unroll
+            for (int j = 0; j < D; ++j) zn[j] = T > 0 ? zs[(int64_t)j * kSweepBlock] : (E)0;
+            for (int t = 0; t < T; ++t) {
+                double z[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = (double)zn[j];
+                if (t + 1 < T) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) zn[j] = zs[(int64_t)((t + 1) * D + j) * kSweepBlock];
+                }
+                if ((t & 31) == 0) word = ys[(int64_t)(t >> 5) * kSweepBlock];
+                const double y = ((word >> (t & 31)) & 1u) ? 1.0 : -1.0;
+                if (NFTL > 0 && do_ftl) Cl = Cl + fabs(dot_seq<D>(z, al) - y);
+#pragma unroll
+                for (int k = 0; k < NF; ++k) Cr[k] = Cr[k] + fabs(dot_seq<D>(z, ar[k]) - y);
+            }
+
+            // ---- results: cum = 0.5*S, comp = 0.5*C (exact), regret = cum - comp (fast_algorithms.py:115)
+            if (NFTL > 0 && do_ftl) {
+                const double cum = 0.5 * Sl, comp = 0.5 * Cl;
+                reg_l = cum - comp;
+                for (int c = 0; c < p.plan.n_ftl; ++c) {
+                    const int64_t o = b * A + p.plan.ftl_col[c];
+                    if (p.regret) p.regret[o] = reg_l;
+                    if (p.cum) p.cum[o] = cum;
+                    if (p.comp) p.comp[o] = comp;
                 }
             }
 #pragma unroll
             for (int k = 0; k < NF; ++k) {
-                const double df = dot_seq<D>(z, x[k]) - y;
-                Sr[k] = Sr[k] + fabs(df);
-                grad_step<D>(thr[k], hz, df);
-            }
-        }
-
-        // ---- pass 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114, 69-76)
-        double ar[NF][D], al[D], Cr[NF], Cl = 0.0;
-#pragma unroll
-        for (int k = 0; k < NF; ++k) { ftl_action<D>(thr[k], ar[k]); Cr[k] = 0.0; }
-        ftl_action<D>(thl, al);
-        st.rewind();
-        for (int t = 0; t < T; ++t) {
-            E ze[D]; E ye;
-            st.next(tb, t, ze, ye);
-            double z[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) z[j] = (double)ze[j];
-            const double y = (double)ye;
-            if (NFTL > 0 && do_ftl) Cl = Cl + fabs(dot_seq<D>(z, al) - y);
-#pragma unroll
-            for (int k = 0; k < NF; ++k) Cr[k] = Cr[k] + fabs(dot_seq<D>(z, ar[k]) - y);
-        }
-
-        // ---- results: cum = 0.5*S, comp = 0.5*C (exact), regret = cum - comp (fast_algorithms.py:115)
-        if (NFTL > 0 && do_ftl) {
-            const double cum = 0.5 * Sl, comp = 0.5 * Cl;
-            reg_l = cum - comp;
-            for (int c = 0; c < p.plan.n_ftl; ++c) {
-                const int64_t o = b * A + p.plan.ftl_col[c];
-                if (p.regret) p.regret[o] = reg_l;
-                if (p.cum) p.cum[o] = cum;
-                if (p.comp) p.comp[o] = comp;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NF; ++k) {
-            if (k < nf) {
-                const double cum = 0.5 * Sr[k], comp = 0.5 * Cr[k];
-                reg_r[k] = cum - comp;
-                const int64_t o = b * A + p.plan.ftrl_col[g * NF + k];
-                if (p.regret) p.regret[o] = reg_r[k];
-                if (p.cum) p.cum[o] = cum;
-                if (p.comp) p.comp[o] = comp;
-            }
-        }
-    }
-
-    // ---- per-block (max, sum, sumsq) of the regrets, fixed order -> deterministic statistics
-    if (p.partials) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
-        for (int s = 0; s < nslots; ++s) {
-            const bool is_ftl = do_ftl && s == nslots - 1;
-            double r = reg_l;
-            if (!is_ftl) {
-#pragma unroll
-                for (int k = 0; k < NF; ++k) if (k == s) r = reg_r[k];
-            }
-            double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
-            double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
-                sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
-                sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
-            }
-            if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
-                for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
-                const int ncols = is_ftl ? p.plan.n_ftl : 1;
-                for (int c = 0; c < ncols; ++c) {
-                    const int col = is_ftl ? p.plan.ftl_col[c] : p.plan.ftrl_col[g * NF + s];
-                    double* o = p.partials + ((int64_t)blockIdx.x * A + col) * 3;
-                    o[0] = m; o[1] = s1; o[2] = s2;
+                if (k < nf) {
+                    const double cum = 0.5 * Sr[k], comp = 0.5 * Cr[k];
+                    reg_r[k] = cum - comp;
+                    const int64_t o = b * A + p.plan.ftrl_col[g * NF + k];
+                    if (p.regret) p.regret[o] = reg_r[k];
+                    if (p.cum) p.cum[o] = cum;
+                    if (p.comp) p.comp[o] = comp;
                 }
             }
-            __syncthreads();
+        }
+
+        // ---- per-chunk (max, sum, sumsq) of the regrets, fixed order -> deterministic statistics
+        if (p.partials) {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
+            for (int s = 0; s < nslots; ++s) {
+                const bool is_ftl = do_ftl && s == nslots - 1;
+                double r = reg_l;
+                if (!is_ftl) {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) if (k == s) r = reg_r[k];
+                }
+                double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
+                double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+                    sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
+                    sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
+                }
+                if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
+                __syncthreads();
+                if (tid == 0) {
+                    double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
+                    for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
+                    const int ncols = is_ftl ? p.plan.n_ftl : 1;
+                    for (int c = 0; c < ncols; ++c) {
+                        const int col = is_ftl ? p.plan.ftl_col[c] : p.plan.ftrl_col[g * NF + s];
+                        double* o = p.partials + (chunk * A + col) * 3;
+                        o[0] = m; o[1] = s1; o[2] = s2;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 }
 
+// persistent launch: one slab per resident CTA; the slab is allocated stream-ordered and freed after the kernel
 template <template <int> class StreamT, int D, int NFTL, int NF>
-static cudaError_t launch_sweep_cfg(const SweepArgs& a, cudaStream_t st) {
-    const unsigned gx = (unsigned)((a.B + kSweepBlock - 1) / kSweepBlock);
-    sweep_kernel<StreamT<D>, D, NFTL, NF><<<dim3(gx, (unsigned)a.plan.groups), kSweepBlock, 0, st>>>(a);
-    return cudaGetLastError();
+static cudaError_t launch_sweep_cfg(SweepArgs a, cudaStream_t st) {
+    typedef typename StreamT<D>::elem_t E;
+    auto kern = sweep_kernel<StreamT<D>, D, NFTL, NF>;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepBlock, 0);
+    if (e != cudaSuccess) return e;
+    const int64_t chunks = (a.B + kSweepBlock - 1) / kSweepBlock;
+    a.n_items = chunks * a.plan.groups;
+    const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
+    const size_t zbytes = (size_t)grid * a.T * D * kSweepBlock * sizeof(E);
+    const size_t ybytes = (size_t)grid * ((a.T + 31) / 32) * kSweepBlock * sizeof(uint32_t);
+    void* slab = nullptr;
+    e = cudaMallocAsync(&slab, zbytes + ybytes + 256, st);
+    if (e != cudaSuccess) return e;
+    a.slab_z = slab;
+    a.slab_y = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(slab) + ((zbytes + 255) / 256) * 256);
+    kern<<<(unsigned)grid, kSweepBlock, 0, st>>>(a);
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(slab, st);
+    return e != cudaSuccess ? e : e2;
 }
 
 template <template <int> class StreamT, int D>

@@ -196,21 +196,31 @@ __global__ void __launch_bounds__(kSweepBlock) sweep_kernel(const SweepArgs p) {
 #pragma unroll
             for (int k = 0; k < NF; ++k) { ftl_action<D>(thr[k], ar[k]); Cr[k] = 0.0; }
             ftl_action<D>(thl, al);
+            // rows are fetched kPF steps at a time: the compare step is only ~5 fp64 ops per variant, so many
+            // loads must be in flight per warp to cover the HBM latency
+            constexpr int kPF = (D == 1) ? 8 : (D == 2 ? 4 : 2);
+            for (int t0 = 0; t0 < T; t0 += kPF) {
+                E zb[kPF][D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) zn[j] = T > 0 ? zs[(int64_t)j * kSweepBlock] : (E)0;
-            for (int t = 0; t < T; ++t) {
-                double z[D];
+                for (int i = 0; i < kPF; ++i) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) z[j] = (double)zn[j];
-                if (t + 1 < T) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) zn[j] = zs[(int64_t)((t + 1) * D + j) * kSweepBlock];
+                    for (int j = 0; j < D; ++j)
+                        zb[i][j] = (t0 + i < T) ? zs[(int64_t)((t0 + i) * D + j) * kSweepBlock] : (E)0;
                 }
-                if ((t & 31) == 0) word = ys[(int64_t)(t >> 5) * kSweepBlock];
-                const double y = ((word >> (t & 31)) & 1u) ? 1.0 : -1.0;
-                if (NFTL > 0 && do_ftl) Cl = Cl + fabs(dot_seq<D>(z, al) - y);
+                if ((t0 & 31) == 0) word = ys[(int64_t)(t0 >> 5) * kSweepBlock];
 #pragma unroll
-                for (int k = 0; k < NF; ++k) Cr[k] = Cr[k] + fabs(dot_seq<D>(z, ar[k]) - y);
+                for (int i = 0; i < kPF; ++i) {
+                    if (t0 + i < T) {
+                        const int t = t0 + i;
+                        double z[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) z[j] = (double)zb[i][j];
+                        const double y = ((word >> (t & 31)) & 1u) ? 1.0 : -1.0;
+                        if (NFTL > 0 && do_ftl) Cl = Cl + fabs(dot_seq<D>(z, al) - y);
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) Cr[k] = Cr[k] + fabs(dot_seq<D>(z, ar[k]) - y);
+                    }
+                }
             }
 
             // ---- results: cum = 0.5*S, comp = 0.5*C (exact), regret = cum - comp (fast_algorithms.py:115)

@@ -44,6 +44,10 @@ WORKLOADS = {
                trials=1_000_000, name="C3 batched d=1 regret sweep: T=1e4 x (FTL + FTRL x 8 eta0 scales)"),
     "c5": dict(d=5, T=10_000, alg=[0], eta=[R2], trials=1_000_000,
                name="C5 empirical g_T sweep: d=5, T=1e4, FTRL eta0=sqrt2"),
+    # streamed: sequences resident in HBM in the reference layout z[B][T][d] (written once by the
+    # generator kernel, untimed); one step = one pass of the TMA-fed FTRL kernel over the resident chunk
+    "c4": dict(d=64, T=10_000, alg=[0], eta=[R2], trials=8192, streamed=True,
+               name="C4 d=64 constrained FTRL on streamed loss vectors (resident chunk of the 1e5-trial job), T=1e4"),
 }
 
 
@@ -94,6 +98,113 @@ def cpu_sweep_rate(wl, budget_s: float, nthreads: int = 0):
     return n * A * wl["T"] / dt, cores, f"{n} of the workload's trials x T={wl['T']} x A={A} (generation + simulation), {dt:.1f} s"
 
 
+def cpu_stream_rate(wl, budget_s: float):
+    """Oracle port of the streamed workload (pre-generated sequences, simulation only)."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = O.num_threads()
+    n = max(cores, 16)
+    zs, ys = zip(*[O.gen_gpath(0, wl["T"], r, wl["d"]) for r in range(n)])
+    z, y = np.stack(zs), np.stack(ys)
+    O.simulate_batch(z[:cores], y[:cores], wl["alg"], wl["eta"])
+    reps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        O.simulate_batch(z, y, wl["alg"], wl["eta"]); reps += 1
+    dt = time.perf_counter() - t0
+    return reps * n * len(wl["alg"]) * wl["T"] / dt, cores, f"{n} resident sequences x T={wl['T']} x d={wl['d']}, {reps} passes, simulation only, {dt:.1f} s"
+
+
+def run_streamed(args, wl):
+    """BASELINE config 4: HBM-resident sequences streamed through the TMA-fed wide-d kernel."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from online_convex_optimization_b200 import engine
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, T, d, A = wl["trials"], wl["T"], wl["d"], len(wl["alg"])
+    mode = args.comparator
+    z, y = engine.gen_sequences_device("gpath", B, T, d, key_a=0, key_c0=rank * B, dtype=torch.float64)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        return engine.simulate_batch_device(z, y, wl["alg"], wl["eta"], comparator=mode)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        reg = step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(); reg = step(); ev[k][1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = float(world) * B * A * T * args.steps / (ms * 1e-3)
+    # e2e: host buffers (pinned) through the host API, PCIe copies inside the timed region, bounded sample
+    nb = min(B, 512)
+    zh = z[:nb].cpu().pin_memory().numpy(); yh = y[:nb].cpu().pin_memory().numpy()
+    engine.simulate_batch(zh[:64], yh[:64], wl["alg"], wl["eta"], comparator=mode, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    out = engine.simulate_batch(zh, yh, wl["alg"], wl["eta"], comparator=mode, device=local)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = float(world) * nb * A * T / float(t.item())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        passes = 1 if mode == "linear" else 2
+        bytes_per_step = (d + 1) * 8 / 1            # SURVEY.md 8(d): compulsory bytes, counted once
+        kernel_rate = B * A * T * args.steps / (ms * 1e-3)
+        achieved = kernel_rate * bytes_per_step / 1e9
+        line = {
+            "metric": "trajectory-steps/sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "trials_per_gpu": B, "T": T, "d": d, "variants": A, "comparator": mode,
+                       "resident_bytes": int(B) * T * (d + 1) * 8,
+                       "l2": "resident chunk (%.1f GB) >> 126 MB L2, plus a 256 MiB flush between timed steps" % (B * T * (d + 1) * 8 / 1e9),
+                       "parallelism": f"dp{world} (independent sequences per rank, no collective)"},
+            "e2e": {"value": e2e_val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(nb) * T * (d + 1) * 8,
+                    "d2h_bytes_per_step": int(nb) * A * 8, "sample": f"{nb} sequences from pinned host memory",
+                    "api": "engine.simulate_batch (oco_simulate_batch_host)"},
+            "gpu_launches": args.steps * 2, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "sim_wide_tma_kernel<2,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
+                         "passes_over_input": passes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "result_check": {"mean_regret": float(reg.mean().item()), "max_regret": float(reg.max().item())},
+        }
+        if world == 1 and not args.no_cpu:
+            v, cores, sample = cpu_stream_rate(wl, min(args.cpu_budget, 10.0))
+            line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args, wl):
     """--impl reference: the CPU port of the same sweep, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -134,12 +245,15 @@ def main():
     ap.add_argument("--trials", type=int, default=0, help="sequences per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--comparator", default="linear", choices=["linear", "two_pass"], help="c4 only")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.trials:
         wl["trials"] = args.trials
     if args.impl == "reference":
         return run_reference(args, wl)
+    if wl.get("streamed"):
+        return run_streamed(args, wl)
 
     import numpy as np
     import torch

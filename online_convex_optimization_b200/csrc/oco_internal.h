@@ -73,6 +73,12 @@ cudaError_t launch_sim_wide(const void* z, const void* y, int in_f32, int64_t B,
                             const Variants& v, const double* scale_tab,
                             double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
                             cudaStream_t st);
+// TMA (1-D bulk async copy + mbarrier) version of launch_sim_wide; requires wide_tma_eligible()
+bool wide_tma_eligible(const void* z, const void* y, int in_f32, int64_t T, int d);
+cudaError_t launch_sim_wide_tma(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                const Variants& v, const double* scale_tab,
+                                double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
+                                cudaStream_t st);
 cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
 // SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).

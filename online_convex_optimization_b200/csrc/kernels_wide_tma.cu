@@ -26,6 +26,7 @@
 //
 // Bytes per trajectory-step: (d+1)*sizeof(TIN) (520 B at d = 64 fp64) -- the roofline figure of
 // SURVEY.md 8(d) -- once in LINEAR mode, twice in TWO_PASS mode.
+#include <cstdlib>
 #include "oco_device.cuh"
 #include "oco_internal.h"
 
@@ -36,6 +37,7 @@ namespace {
 constexpr int kWarps = 8;      // warps (trajectories) per CTA
 constexpr int kTT = 4;         // rows per tile: TT*sizeof(TIN) is a multiple of 16 for fp32 and fp64
 constexpr int kStages = 3;
+
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,14 +71,18 @@ struct WideTmaArgs {
     Variants v;
 };
 
-__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
+// two fp64 warp sums for the price of ~1.2: after the first exchange the low half-warp carries `a`
+// and the high half-warp carries `b`; four more exchanges finish both, one more redistributes.
+__device__ __forceinline__ void warp_sum2(double& a, double& b, int lane) {
+    const bool hi = (lane & 16) != 0;
+    double keep = hi ? b : a;
+    const double send = hi ? a : b;
+    keep = keep + __shfl_xor_sync(0xffffffffu, send, 16);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double a2 = __shfl_xor_sync(0xffffffffu, a, off);
-        const double b2 = __shfl_xor_sync(0xffffffffu, b, off);
-        const double c2 = __shfl_xor_sync(0xffffffffu, c, off);
-        a = a + a2; b = b + b2; c = c + c2;
-    }
+    for (int off = 8; off > 0; off >>= 1) keep = keep + __shfl_xor_sync(0xffffffffu, keep, off);
+    const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
+    a = hi ? other : keep;
+    b = hi ? keep : other;
 }
 __device__ __forceinline__ double warp_sum1(double a) {
 #pragma unroll
@@ -84,91 +90,96 @@ __device__ __forceinline__ double warp_sum1(double a) {
     return a;
 }
 
-template <int K, typename TIN>
-__global__ void __launch_bounds__(kWarps * 32, (K <= 2 ? 4 : 1)) sim_wide_tma_kernel(const WideTmaArgs p) {
+// One warp per trajectory; D (multiple of 32) is a template parameter so that every shared-memory
+// address is an immediate offset from one per-lane base pointer.
+template <int D, typename TIN>
+__global__ void __launch_bounds__(kWarps * 32, (D <= 64 ? 4 : (D <= 128 ? 2 : 1))) sim_wide_tma_kernel(const WideTmaArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[kWarps][kStages];
+    constexpr int K = D / 32;
+    constexpr uint32_t z_tile_bytes = kTT * D * sizeof(TIN);
+    constexpr uint32_t y_tile_bytes = kTT * sizeof(TIN);
+    constexpr uint32_t stage_bytes = z_tile_bytes + y_tile_bytes;
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int A = p.v.A, T = p.T;
     const int64_t w = (int64_t)blockIdx.x * kWarps + wib;
-    const int A = p.v.A, d = p.d, T = p.T;
-    const bool valid = w < p.B * A;
-    const int64_t b = valid ? w / A : 0;
-    const int a = valid ? (int)(w - b * A) : 0;
-    const bool ftrl = p.v.alg_flag[a] == 0;
-    const TIN* __restrict__ zb = (const TIN*)p.z + b * (int64_t)T * d;
-    const TIN* __restrict__ yb = (const TIN*)p.y + b * (int64_t)T;
-
-    const uint32_t z_tile_bytes = (uint32_t)(kTT * d * sizeof(TIN));
-    const uint32_t y_tile_bytes = (uint32_t)(kTT * sizeof(TIN));
-    const uint32_t stage_bytes = z_tile_bytes + y_tile_bytes;
-    unsigned char* my_smem = smem_raw + (size_t)wib * kStages * stage_bytes;
+    unsigned char* warp_smem = smem_raw + (size_t)wib * kStages * stage_bytes;
     uint64_t* my_bars = bars[wib];
-
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&my_bars[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    if (!valid) return;
+    if (w >= p.B * A) return;
+    const int64_t b = w / A;
+    const int a = (int)(w - b * A);
+    const bool ftrl = p.v.alg_flag[a] == 0;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * (int64_t)T * D;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * (int64_t)T;
 
     const int ntiles = T / kTT;
-    uint32_t consumed = 0, issued = 0;       // running tile counters across passes -> stage and parity
+    int cs = 0, is = 0;                        // consumer / producer stage cursors
+    uint32_t cparity = 0;
 
-    auto issue = [&](int tile) {             // lane 0 only
-        const int s = issued % kStages;
-        unsigned char* dst = my_smem + (size_t)s * stage_bytes;
-        mbar_arrive_expect_tx(&my_bars[s], stage_bytes);
-        bulk_g2s(dst, zb + (int64_t)tile * kTT * d, z_tile_bytes, &my_bars[s]);
-        bulk_g2s(dst + z_tile_bytes, yb + (int64_t)tile * kTT, y_tile_bytes, &my_bars[s]);
-        ++issued;
+    auto issue = [&](int tile) {               // lane 0 only
+        unsigned char* dst = warp_smem + is * stage_bytes;
+        mbar_arrive_expect_tx(&my_bars[is], stage_bytes);
+        bulk_g2s(dst, zb + (int64_t)tile * (kTT * D), z_tile_bytes, &my_bars[is]);
+        bulk_g2s(dst + z_tile_bytes, yb + (int64_t)tile * kTT, y_tile_bytes, &my_bars[is]);
+        is = (is + 1 == kStages) ? 0 : is + 1;
     };
 
     double th[K], vy[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { th[k] = 0.0; vy[k] = 0.0; }
-    double S = 0.0;                          // sum |q - y| ; cum_loss = 0.5 * S (exact)
+    double S = 0.0;                            // sum |q - y| ; cum_loss = 0.5 * S (exact)
     bool linear_ok = true;
     const bool want_linear = p.comparator_mode == 1;
+    const double* __restrict__ tabp = p.tab + a;
 
-    auto play_row = [&](const double (&z)[K], double y, int t) {
-        double x[K], n2 = 0.0, zx = 0.0, zz = 0.0;
+    auto play_row = [&](const double (&z)[K], double y) {
+        double x[K], n2 = 0.0, zx = 0.0;
         if (ftrl) {
-            const double sc = __ldg(p.tab + (int64_t)t * A + a);
+            const double sc = __ldg(tabp);
 #pragma unroll
             for (int k = 0; k < K; ++k) x[k] = sc * th[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < K; ++k) x[k] = th[k];      // direction only; normalised below
+            for (int k = 0; k < K; ++k) x[k] = th[k];        // direction only; normalised below
         }
+        tabp += A;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { n2 = n2 + x[k] * x[k]; zx = zx + z[k] * x[k]; zz = zz + z[k] * z[k]; }
-        warp_sum3(n2, zx, zz);
-        double q;
-        if (ftrl) q = (n2 <= 1.0) ? zx : zx * (1.0 / sqrt(n2));                 // fast_algorithms.py:61-66
+        for (int k = 0; k < K; ++k) { n2 = n2 + x[k] * x[k]; zx = zx + z[k] * x[k]; }
+        warp_sum2(n2, zx, lane);
+        double q = zx;
+        if (ftrl) { if (!(n2 <= 1.0)) q = zx * (1.0 / sqrt(n2)); }              // fast_algorithms.py:61-66 (warp-uniform)
         else q = (n2 == 0.0) ? 0.0 : zx * -(1.0 / sqrt(n2));                    // fast_algorithms.py:44-49
         const double df = q - y;
         S = S + fabs(df);
-        if (df > 0.0 || df < 0.0) {
-            const double g = df > 0.0 ? 0.5 : -0.5;
+        const double g = df > 0.0 ? 0.5 : (df < 0.0 ? -0.5 : 0.0);
 #pragma unroll
-            for (int k = 0; k < K; ++k) th[k] = th[k] + g * z[k];
-        }
+        for (int k = 0; k < K; ++k) th[k] = th[k] + g * z[k];
         if (want_linear) {
-            if (!(zz <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) linear_ok = false;
+            // precondition of the linear comparator: ||z_t||^2 <= 1 (+1e-6) and y = +-1.  The squared
+            // norm is reduced in 2^-24 fixed point with ONE integer REDUX instead of ten shuffles.
+            double zz = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) zz = zz + z[k] * z[k];
+            const unsigned tot = __reduce_add_sync(0xffffffffu, __double2uint_rz(fmin(zz, 4.0) * 16777216.0));
+            if (tot > 16777216u + 17u || !(y == 1.0 || y == -1.0)) linear_ok = false;
 #pragma unroll
             for (int k = 0; k < K; ++k) vy[k] = vy[k] + y * z[k];
         }
     };
 
     double act[K], C = 0.0;
-    auto compare_row = [&](const double (&z)[K], double y, int) {
+    auto compare_row = [&](const double (&z)[K], double y) {
         double q = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) q = q + z[k] * act[k];
-        q = warp_sum1(q);
-        C = C + fabs(q - y);
+        C = C + fabs(warp_sum1(q) - y);
     };
 
     auto stream_pass = [&](auto&& row_fn) {
@@ -177,26 +188,25 @@ __global__ void __launch_bounds__(kWarps * 32, (K <= 2 ? 4 : 1)) sim_wide_tma_ke
             for (int i = 0; i < pre; ++i) issue(i);
         }
         for (int tile = 0; tile < ntiles; ++tile) {
-            const int s = consumed % kStages;
-            mbar_wait(&my_bars[s], (consumed / kStages) & 1u);
-            const TIN* zt = reinterpret_cast<const TIN*>(my_smem + (size_t)s * stage_bytes);
-            const TIN* yt = reinterpret_cast<const TIN*>(my_smem + (size_t)s * stage_bytes + z_tile_bytes);
+            mbar_wait(&my_bars[cs], cparity);
+            const TIN* zt = reinterpret_cast<const TIN*>(warp_smem + cs * stage_bytes) + lane;
+            const TIN* yt = reinterpret_cast<const TIN*>(warp_smem + cs * stage_bytes + z_tile_bytes);
 #pragma unroll
             for (int r = 0; r < kTT; ++r) {
                 double z[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; z[k] = (j < d) ? (double)zt[r * d + j] : 0.0; }
-                row_fn(z, (double)yt[r], tile * kTT + r);
+                for (int k = 0; k < K; ++k) z[k] = (double)zt[r * D + 32 * k];
+                row_fn(z, (double)yt[r]);
             }
-            ++consumed;
+            if (++cs == kStages) { cs = 0; cparity ^= 1u; }
             __syncwarp();
             if (lane == 0 && tile + kStages < ntiles) issue(tile + kStages);
         }
-        for (int t = ntiles * kTT; t < T; ++t) {            // ragged tail: direct loads
+        for (int t = ntiles * kTT; t < T; ++t) {              // ragged tail: direct loads
             double z[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; z[k] = (j < d) ? (double)zb[(int64_t)t * d + j] : 0.0; }
-            row_fn(z, (double)yb[t], t);
+            for (int k = 0; k < K; ++k) z[k] = (double)zb[(int64_t)t * D + lane + 32 * k];
+            row_fn(z, (double)yb[t]);
         }
     };
 
@@ -216,8 +226,7 @@ __global__ void __launch_bounds__(kWarps * 32, (K <= 2 ? 4 : 1)) sim_wide_tma_ke
         double av = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) av = av + act[k] * vy[k];
-        av = warp_sum1(av);
-        comp = 0.5 * ((double)T - av);
+        comp = 0.5 * ((double)T - warp_sum1(av));
     } else {
         stream_pass(compare_row);
         comp = 0.5 * C;
@@ -230,16 +239,16 @@ __global__ void __launch_bounds__(kWarps * 32, (K <= 2 ? 4 : 1)) sim_wide_tma_ke
     }
     if (p.theta_final) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) { const int j = lane + 32 * k; if (j < d) p.theta_final[w * d + j] = th[k]; }
+        for (int k = 0; k < K; ++k) p.theta_final[w * D + lane + 32 * k] = th[k];
     }
 }
 
-template <int K, typename TIN>
+template <int D, typename TIN>
 cudaError_t launch_k(const WideTmaArgs& a, cudaStream_t st) {
     const int64_t nw = a.B * a.v.A;
     const unsigned gx = (unsigned)((nw + kWarps - 1) / kWarps);
-    const size_t smem = (size_t)kWarps * kStages * (kTT * (a.d + 1) * sizeof(TIN));
-    auto kern = sim_wide_tma_kernel<K, TIN>;
+    const size_t smem = (size_t)kWarps * kStages * (kTT * (D + 1) * sizeof(TIN));
+    auto kern = sim_wide_tma_kernel<D, TIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<gx, kWarps * 32, smem, st>>>(a);
@@ -248,12 +257,11 @@ cudaError_t launch_k(const WideTmaArgs& a, cudaStream_t st) {
 
 template <typename TIN>
 cudaError_t launch_t(const WideTmaArgs& a, cudaStream_t st) {
-    switch ((a.d + 31) / 32) {
-    case 1: return launch_k<1, TIN>(a, st);
-    case 2: return launch_k<2, TIN>(a, st);
-    case 3: return launch_k<3, TIN>(a, st);
-    case 4: return launch_k<4, TIN>(a, st);
-    case 5: case 6: case 7: case 8: return launch_k<8, TIN>(a, st);
+    switch (a.d) {
+    case 32: return launch_k<32, TIN>(a, st);
+    case 64: return launch_k<64, TIN>(a, st);
+    case 128: return launch_k<128, TIN>(a, st);
+    case 256: return launch_k<256, TIN>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -266,7 +274,7 @@ bool wide_tma_eligible(const void* z, const void* y, int in_f32, int64_t T, int 
     const size_t es = in_f32 ? 4 : 8;
     return ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((size_t)d * es) % 16 == 0 &&
            ((size_t)T * es) % 16 == 0 && T < 0x7fffffff &&
-           (size_t)kWarps * kStages * (kTT * (d + 1) * es) <= 200 * 1024;
+           (d == 32 || d == 64 || d == 128 || d == 256);
 }
 
 cudaError_t launch_sim_wide_tma(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,

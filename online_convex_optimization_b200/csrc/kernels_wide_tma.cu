@@ -27,6 +27,7 @@
 // Bytes per trajectory-step: (d+1)*sizeof(TIN) (520 B at d = 64 fp64) -- the roofline figure of
 // SURVEY.md 8(d) -- once in LINEAR mode, twice in TWO_PASS mode.
 #include <cstdlib>
+#include <type_traits>
 #include "oco_device.cuh"
 #include "oco_internal.h"
 
@@ -36,7 +37,7 @@ namespace {
 
 constexpr int kWarps = 8;      // warps (trajectories) per CTA
 constexpr int kTT = 4;         // rows per tile: TT*sizeof(TIN) is a multiple of 16 for fp32 and fp64
-constexpr int kStages = 3;
+constexpr int kStages = 2;
 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,184 +72,256 @@ struct WideTmaArgs {
     Variants v;
 };
 
-// two fp64 warp sums for the price of ~1.2: after the first exchange the low half-warp carries `a`
-// and the high half-warp carries `b`; four more exchanges finish both, one more redistributes.
-__device__ __forceinline__ void warp_sum2(double& a, double& b, int lane) {
-    const bool hi = (lane & 16) != 0;
+// Reductions confined to groups of G lanes (G lanes cooperate on one trajectory).
+// group_sum2: two fp64 sums for the price of ~1.2 -- after the first exchange the low half of the
+// group carries `a` and the high half carries `b`; log2(G)-1 more exchanges finish both, one more
+// redistributes.
+template <int G>
+__device__ __forceinline__ void group_sum2(double& a, double& b, int sl) {
+    const bool hi = (sl & (G / 2)) != 0;
     double keep = hi ? b : a;
     const double send = hi ? a : b;
-    keep = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    keep = keep + __shfl_xor_sync(0xffffffffu, send, G / 2);
 #pragma unroll
-    for (int off = 8; off > 0; off >>= 1) keep = keep + __shfl_xor_sync(0xffffffffu, keep, off);
-    const double other = __shfl_xor_sync(0xffffffffu, keep, 16);
+    for (int off = G / 4; off > 0; off >>= 1) keep = keep + __shfl_xor_sync(0xffffffffu, keep, off);
+    const double other = __shfl_xor_sync(0xffffffffu, keep, G / 2);
     a = hi ? other : keep;
     b = hi ? keep : other;
 }
-__device__ __forceinline__ double warp_sum1(double a) {
+template <int G>
+__device__ __forceinline__ double group_sum1(double a) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a = a + __shfl_xor_sync(0xffffffffu, a, off);
+    for (int off = G / 2; off > 0; off >>= 1) a = a + __shfl_xor_sync(0xffffffffu, a, off);
     return a;
 }
 
-// One warp per trajectory; D (multiple of 32) is a template parameter so that every shared-memory
-// address is an immediate offset from one per-lane base pointer.
-template <int D, typename TIN>
-__global__ void __launch_bounds__(kWarps * 32, (D <= 64 ? 4 : (D <= 128 ? 2 : 1))) sim_wide_tma_kernel(const WideTmaArgs p) {
+// ---- per-trajectory state (G lanes hold K = D/G elements each, element j = sl + G*k)
+// State is kept doubled: th2 = 2*theta accumulates +-z_t (a sign flip and one DADD per element; the
+// factor 0.5 of the gradient is folded into the per-step scale, an exact power-of-two scaling),
+// vy = sum y_t z_t likewise (labels are +-1 whenever the linear comparator is usable).
+template <int K>
+struct WideState {
+    double th2[K], vy[K], act[K];
+    double S, C;                 // sum |q - y| over the played / comparator actions (losses are 0.5 * these)
+    bool linear_ok;
+    const double* tabp;          // walks the [T][A] FTRL scale table
+};
+
+__device__ __forceinline__ double flip_sign(double v, int sgn) {
+    return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v));
+}
+
+// one round of play; MODE 0: every trajectory of the warp is FTRL, 1: all FTL, 2: mixed (per-lane select)
+template <int MODE, int G, int K>
+__device__ __forceinline__ void play_row(WideState<K>& st, const double (&z)[K], double y, bool ftrl, bool want_linear,
+                                         int A, int sl, int grp) {
+    constexpr int NT = 32 / G;
+    const bool is_ftrl = MODE == 0 || (MODE == 2 && ftrl);
+    double x[K];
+    if (MODE != 1) {
+        const double sc = 0.5 * __ldg(st.tabp);              // x = (0.5*scale) * (2*theta)
+        st.tabp += A;
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = (MODE == 0 || ftrl) ? sc * st.th2[k] : st.th2[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = st.th2[k];        // FTL: direction only, normalised below
+    }
+    double n2 = x[0] * x[0], zx = z[0] * x[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) { n2 = n2 + x[k] * x[k]; zx = zx + z[k] * x[k]; }
+    group_sum2<G>(n2, zx, sl);
+    double q = zx;
+    if (is_ftrl) { if (!(n2 <= 1.0)) q = zx * (1.0 / sqrt(n2)); }               // fast_algorithms.py:61-66
+    else q = (n2 == 0.0) ? 0.0 : zx * -(1.0 / sqrt(n2));                        // fast_algorithms.py:44-49
+    const double df = q - y;
+    st.S = st.S + fabs(df);
+    if (df > 0.0 || df < 0.0) {                              // theta += 0.5*sign(df)*z  <=>  th2 += sign(df)*z
+        const int sgn = __double2hiint(df) & 0x80000000;
+#pragma unroll
+        for (int k = 0; k < K; ++k) st.th2[k] = st.th2[k] + flip_sign(z[k], sgn);
+    }
+    if (want_linear) {
+        // precondition of the linear comparator: ||z_t||^2 <= 1 (+1e-6) and y = +-1.  The squared norm is
+        // reduced in 2^-24 fixed point with one full-warp integer REDUX per trajectory of the warp.
+        double zz = z[0] * z[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) zz = zz + z[k] * z[k];
+        const unsigned units = __double2uint_rz(fmin(zz, 4.0) * 16777216.0);
+        unsigned tot = 0;
+#pragma unroll
+        for (int g = 0; g < NT; ++g) {
+            const unsigned tg = __reduce_add_sync(0xffffffffu, grp == g ? units : 0u);
+            if (grp == g) tot = tg;
+        }
+        if (tot > 16777216u + 17u || !(y == 1.0 || y == -1.0)) st.linear_ok = false;
+        const int ysgn = __double2hiint(y) & 0x80000000;
+#pragma unroll
+        for (int k = 0; k < K; ++k) st.vy[k] = st.vy[k] + flip_sign(z[k], ysgn);
+    }
+}
+
+template <int G, int K>
+__device__ __forceinline__ void compare_row(WideState<K>& st, const double (&z)[K], double y) {
+    double q = z[0] * st.act[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) q = q + z[k] * st.act[k];
+    st.C = st.C + fabs(group_sum1<G>(q) - y);
+}
+
+// ---- the per-warp TMA ring
+template <int D, int G, typename TIN>
+struct WidePipe {
+    static constexpr int NT = 32 / G;
+    static constexpr uint32_t z_tile_bytes = kTT * D * sizeof(TIN);
+    static constexpr uint32_t y_tile_bytes = kTT * sizeof(TIN);
+    static constexpr uint32_t traj_bytes = z_tile_bytes + y_tile_bytes;
+    static constexpr uint32_t stage_bytes = traj_bytes * NT;
+    unsigned char* smem; uint64_t* bars;
+    const TIN* z; const TIN* y;       // batch base pointers
+    int64_t w0; int A, T, nvalid;
+    int cs, is; uint32_t cparity;
+
+    __device__ __forceinline__ void issue(int tile) {        // lane 0 only: the NT tiles of a stage complete on one barrier
+        unsigned char* dst = smem + is * stage_bytes;
+        mbar_arrive_expect_tx(&bars[is], traj_bytes * (uint32_t)nvalid);
+#pragma unroll
+        for (int g = 0; g < NT; ++g) {
+            if (g < nvalid) {
+                const int64_t bg = (w0 + g) / A;
+                bulk_g2s(dst + g * traj_bytes, z + (bg * T + (int64_t)tile * kTT) * D, z_tile_bytes, &bars[is]);
+                bulk_g2s(dst + g * traj_bytes + z_tile_bytes, y + bg * T + (int64_t)tile * kTT, y_tile_bytes, &bars[is]);
+            }
+        }
+        is = (is + 1 == kStages) ? 0 : is + 1;
+    }
+};
+
+// PASS 0/1/2: play with that MODE; PASS 3: comparator pass
+template <int PASS, int D, int G, typename TIN>
+__device__ __forceinline__ void stream_pass(WidePipe<D, G, TIN>& pp, WideState<D / G>& st, const TIN* zb, const TIN* yb,
+                                            bool ftrl, bool want_linear, bool valid, int lane, int sl, int grp) {
+    constexpr int K = D / G;
+    typedef WidePipe<D, G, TIN> P;
+    const int ntiles = pp.T / kTT;
+    if (lane == 0) {
+        const int pre = ntiles < kStages ? ntiles : kStages;
+        for (int i = 0; i < pre; ++i) pp.issue(i);
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+        mbar_wait(&pp.bars[pp.cs], pp.cparity);
+        const unsigned char* base = pp.smem + pp.cs * P::stage_bytes + (valid ? grp : 0) * P::traj_bytes;
+        const TIN* zt = reinterpret_cast<const TIN*>(base) + sl;
+        const TIN* yt = reinterpret_cast<const TIN*>(base + P::z_tile_bytes);
+#pragma unroll
+        for (int r = 0; r < kTT; ++r) {
+            double z[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) z[k] = (double)zt[r * D + G * k];
+            if (PASS == 3) compare_row<G, K>(st, z, (double)yt[r]);
+            else play_row<PASS, G, K>(st, z, (double)yt[r], ftrl, want_linear, pp.A, sl, grp);
+        }
+        if (++pp.cs == kStages) { pp.cs = 0; pp.cparity ^= 1u; }
+        __syncwarp();
+        if (lane == 0 && tile + kStages < ntiles) pp.issue(tile + kStages);
+    }
+    for (int t = ntiles * kTT; t < pp.T; ++t) {              // ragged tail: direct loads
+        double z[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) z[k] = (double)zb[(int64_t)t * D + sl + G * k];
+        if (PASS == 3) compare_row<G, K>(st, z, (double)yb[t]);
+        else play_row<PASS, G, K>(st, z, (double)yb[t], ftrl, want_linear, pp.A, sl, grp);
+    }
+}
+
+// G lanes per trajectory, NT = 32/G trajectories per warp.  The per-step warp-level overhead (shuffles,
+// selects, barrier polling, loop control) is shared by the NT trajectories of a warp, which is what
+// brings the instruction count per trajectory-step under the HBM-roofline budget (~90 issue slots at
+// d = 64).  D is a template parameter so that every shared-memory address is an immediate offset.
+template <int D, int G, typename TIN>
+__global__ void __launch_bounds__(kWarps * 32, (D / G <= 2 ? 4 : (D / G <= 4 ? 3 : 1))) sim_wide_tma_kernel(const WideTmaArgs p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[kWarps][kStages];
-    constexpr int K = D / 32;
-    constexpr uint32_t z_tile_bytes = kTT * D * sizeof(TIN);
-    constexpr uint32_t y_tile_bytes = kTT * sizeof(TIN);
-    constexpr uint32_t stage_bytes = z_tile_bytes + y_tile_bytes;
+    constexpr int K = D / G, NT = 32 / G;
+    typedef WidePipe<D, G, TIN> P;
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / G, sl = lane % G;
     const int A = p.v.A, T = p.T;
-    const int64_t w = (int64_t)blockIdx.x * kWarps + wib;
-    unsigned char* warp_smem = smem_raw + (size_t)wib * kStages * stage_bytes;
-    uint64_t* my_bars = bars[wib];
+    const int64_t total = p.B * A;
+    const int64_t w0 = ((int64_t)blockIdx.x * kWarps + wib) * NT;
+    P pp;
+    pp.smem = smem_raw + (size_t)wib * kStages * P::stage_bytes;
+    pp.bars = bars[wib];
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&my_bars[s], 1);
+        for (int s = 0; s < kStages; ++s) mbar_init(&pp.bars[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
-    if (w >= p.B * A) return;
-    const int64_t b = w / A;
-    const int a = (int)(w - b * A);
+    if (w0 >= total) return;
+    pp.z = (const TIN*)p.z; pp.y = (const TIN*)p.y; pp.w0 = w0; pp.A = A; pp.T = T;
+    pp.nvalid = (int)((total - w0) < NT ? (total - w0) : NT);
+    pp.cs = 0; pp.is = 0; pp.cparity = 0;
+    const int64_t w = w0 + grp;
+    const bool valid = grp < pp.nvalid;
+    const int64_t b = valid ? w / A : 0;
+    const int a = valid ? (int)(w - b * A) : 0;
     const bool ftrl = p.v.alg_flag[a] == 0;
     const TIN* __restrict__ zb = (const TIN*)p.z + b * (int64_t)T * D;
     const TIN* __restrict__ yb = (const TIN*)p.y + b * (int64_t)T;
-
-    const int ntiles = T / kTT;
-    int cs = 0, is = 0;                        // consumer / producer stage cursors
-    uint32_t cparity = 0;
-
-    auto issue = [&](int tile) {               // lane 0 only
-        unsigned char* dst = warp_smem + is * stage_bytes;
-        mbar_arrive_expect_tx(&my_bars[is], stage_bytes);
-        bulk_g2s(dst, zb + (int64_t)tile * (kTT * D), z_tile_bytes, &my_bars[is]);
-        bulk_g2s(dst + z_tile_bytes, yb + (int64_t)tile * kTT, y_tile_bytes, &my_bars[is]);
-        is = (is + 1 == kStages) ? 0 : is + 1;
-    };
-
-    double th[K], vy[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { th[k] = 0.0; vy[k] = 0.0; }
-    double S = 0.0;                            // sum |q - y| ; cum_loss = 0.5 * S (exact)
-    bool linear_ok = true;
     const bool want_linear = p.comparator_mode == 1;
-    const double* __restrict__ tabp = p.tab + a;
 
-    auto play_row = [&](const double (&z)[K], double y) {
-        double x[K], n2 = 0.0, zx = 0.0;
-        if (ftrl) {
-            const double sc = __ldg(tabp);
+    WideState<K> st;
 #pragma unroll
-            for (int k = 0; k < K; ++k) x[k] = sc * th[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) x[k] = th[k];        // direction only; normalised below
-        }
-        tabp += A;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { n2 = n2 + x[k] * x[k]; zx = zx + z[k] * x[k]; }
-        warp_sum2(n2, zx, lane);
-        double q = zx;
-        if (ftrl) { if (!(n2 <= 1.0)) q = zx * (1.0 / sqrt(n2)); }              // fast_algorithms.py:61-66 (warp-uniform)
-        else q = (n2 == 0.0) ? 0.0 : zx * -(1.0 / sqrt(n2));                    // fast_algorithms.py:44-49
-        const double df = q - y;
-        S = S + fabs(df);
-        const double g = df > 0.0 ? 0.5 : (df < 0.0 ? -0.5 : 0.0);
-#pragma unroll
-        for (int k = 0; k < K; ++k) th[k] = th[k] + g * z[k];
-        if (want_linear) {
-            // precondition of the linear comparator: ||z_t||^2 <= 1 (+1e-6) and y = +-1.  The squared
-            // norm is reduced in 2^-24 fixed point with ONE integer REDUX instead of ten shuffles.
-            double zz = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) zz = zz + z[k] * z[k];
-            const unsigned tot = __reduce_add_sync(0xffffffffu, __double2uint_rz(fmin(zz, 4.0) * 16777216.0));
-            if (tot > 16777216u + 17u || !(y == 1.0 || y == -1.0)) linear_ok = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) vy[k] = vy[k] + y * z[k];
-        }
-    };
+    for (int k = 0; k < K; ++k) { st.th2[k] = 0.0; st.vy[k] = 0.0; st.act[k] = 0.0; }
+    st.S = 0.0; st.C = 0.0; st.linear_ok = true; st.tabp = p.tab + a;
 
-    double act[K], C = 0.0;
-    auto compare_row = [&](const double (&z)[K], double y) {
-        double q = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) q = q + z[k] * act[k];
-        C = C + fabs(warp_sum1(q) - y);
-    };
+    // all trajectories of the warp run the same algorithm? then the step has no per-lane algorithm select
+    if (__all_sync(0xffffffffu, ftrl || !valid)) stream_pass<0, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
+    else if (__all_sync(0xffffffffu, !ftrl || !valid)) stream_pass<1, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
+    else stream_pass<2, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
 
-    auto stream_pass = [&](auto&& row_fn) {
-        if (lane == 0) {
-            const int pre = ntiles < kStages ? ntiles : kStages;
-            for (int i = 0; i < pre; ++i) issue(i);
-        }
-        for (int tile = 0; tile < ntiles; ++tile) {
-            mbar_wait(&my_bars[cs], cparity);
-            const TIN* zt = reinterpret_cast<const TIN*>(warp_smem + cs * stage_bytes) + lane;
-            const TIN* yt = reinterpret_cast<const TIN*>(warp_smem + cs * stage_bytes + z_tile_bytes);
+    {   // comparator = FTL action of the final theta (fast_algorithms.py:113); scale-invariant in theta
+        double n2 = st.th2[0] * st.th2[0];
 #pragma unroll
-            for (int r = 0; r < kTT; ++r) {
-                double z[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) z[k] = (double)zt[r * D + 32 * k];
-                row_fn(z, (double)yt[r]);
-            }
-            if (++cs == kStages) { cs = 0; cparity ^= 1u; }
-            __syncwarp();
-            if (lane == 0 && tile + kStages < ntiles) issue(tile + kStages);
-        }
-        for (int t = ntiles * kTT; t < T; ++t) {              // ragged tail: direct loads
-            double z[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) z[k] = (double)zb[(int64_t)t * D + lane + 32 * k];
-            row_fn(z, (double)yb[t]);
-        }
-    };
-
-    stream_pass(play_row);
-
-    {   // comparator = FTL action of the final theta (fast_algorithms.py:113)
-        double n2 = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) n2 = n2 + th[k] * th[k];
-        n2 = warp_sum1(n2);
+        for (int k = 1; k < K; ++k) n2 = n2 + st.th2[k] * st.th2[k];
+        n2 = group_sum1<G>(n2);
         const double sc = (n2 == 0.0) ? 0.0 : -(1.0 / sqrt(n2));
 #pragma unroll
-        for (int k = 0; k < K; ++k) act[k] = (n2 == 0.0) ? 0.0 : sc * th[k];
+        for (int k = 0; k < K; ++k) st.act[k] = (n2 == 0.0) ? 0.0 : sc * st.th2[k];
     }
+    // the second pass shares the warp's barriers: taken if ANY trajectory of the warp needs it
+    const bool use_linear = want_linear && st.linear_ok;
+    if (__any_sync(0xffffffffu, valid && !use_linear)) stream_pass<3, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
     double comp;
-    if (want_linear && linear_ok) {
-        double av = 0.0;
+    if (use_linear) {
+        double av = st.act[0] * st.vy[0];
 #pragma unroll
-        for (int k = 0; k < K; ++k) av = av + act[k] * vy[k];
-        comp = 0.5 * ((double)T - warp_sum1(av));
+        for (int k = 1; k < K; ++k) av = av + st.act[k] * st.vy[k];
+        comp = 0.5 * ((double)T - group_sum1<G>(av));
     } else {
-        stream_pass(compare_row);
-        comp = 0.5 * C;
+        comp = 0.5 * st.C;
     }
-    const double cum = 0.5 * S;
-    if (lane == 0) {
+    const double cum = 0.5 * st.S;
+    if (valid && sl == 0) {
         if (p.regret) p.regret[w] = cum - comp;
         if (p.cum) p.cum[w] = cum;
         if (p.comp) p.comp[w] = comp;
     }
-    if (p.theta_final) {
+    if (valid && p.theta_final) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) p.theta_final[w * D + lane + 32 * k] = th[k];
+        for (int k = 0; k < K; ++k) p.theta_final[w * D + sl + G * k] = 0.5 * st.th2[k];
     }
 }
 
-template <int D, typename TIN>
+template <int D, int G, typename TIN>
 cudaError_t launch_k(const WideTmaArgs& a, cudaStream_t st) {
-    const int64_t nw = a.B * a.v.A;
+    constexpr int NT = 32 / G;
+    const int64_t nw = (a.B * a.v.A + NT - 1) / NT;
     const unsigned gx = (unsigned)((nw + kWarps - 1) / kWarps);
-    const size_t smem = (size_t)kWarps * kStages * (kTT * (D + 1) * sizeof(TIN));
-    auto kern = sim_wide_tma_kernel<D, TIN>;
+    const size_t smem = (size_t)kWarps * kStages * NT * (kTT * (D + 1) * sizeof(TIN));
+    auto kern = sim_wide_tma_kernel<D, G, TIN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<gx, kWarps * 32, smem, st>>>(a);
@@ -257,11 +330,12 @@ cudaError_t launch_k(const WideTmaArgs& a, cudaStream_t st) {
 
 template <typename TIN>
 cudaError_t launch_t(const WideTmaArgs& a, cudaStream_t st) {
+    static const int g64 = [] { const char* e = getenv("OCO_WIDE_G"); return e ? atoi(e) : 16; }();   // tuning knob
     switch (a.d) {
-    case 32: return launch_k<32, TIN>(a, st);
-    case 64: return launch_k<64, TIN>(a, st);
-    case 128: return launch_k<128, TIN>(a, st);
-    case 256: return launch_k<256, TIN>(a, st);
+    case 32: return launch_k<32, 8, TIN>(a, st);
+    case 64: return g64 == 32 ? launch_k<64, 32, TIN>(a, st) : (g64 == 8 ? launch_k<64, 8, TIN>(a, st) : launch_k<64, 16, TIN>(a, st));
+    case 128: return launch_k<128, 32, TIN>(a, st);
+    case 256: return launch_k<256, 32, TIN>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }

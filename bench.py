@@ -46,7 +46,7 @@ WORKLOADS = {
                name="C5 empirical g_T sweep: d=5, T=1e4, FTRL eta0=sqrt2"),
     # streamed: sequences resident in HBM in the reference layout z[B][T][d] (written once by the
     # generator kernel, untimed); one step = one pass of the TMA-fed FTRL kernel over the resident chunk
-    "c4": dict(d=64, T=10_000, alg=[0], eta=[R2], trials=8192, streamed=True,
+    "c4": dict(d=64, T=10_000, alg=[0], eta=[R2], trials=14208, streamed=True,   # 2 full waves of 3 CTAs x 148 SMs x 16 trajectories
                name="C4 d=64 constrained FTRL on streamed loss vectors (resident chunk of the 1e5-trial job), T=1e4"),
 }
 
@@ -114,7 +114,7 @@ def cpu_stream_rate(wl, budget_s: float):
     return reps * n * len(wl["alg"]) * wl["T"] / dt, cores, f"{n} resident sequences x T={wl['T']} x d={wl['d']}, {reps} passes, simulation only, {dt:.1f} s"
 
 
-def run_streamed(args, wl):
+def run_streamed(args, wl, *, emit=True, init_dist=True):
     """BASELINE config 4: HBM-resident sequences streamed through the TMA-fed wide-d kernel."""
     import numpy as np
     import torch
@@ -123,7 +123,7 @@ def run_streamed(args, wl):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and init_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, T, d, A = wl["trials"], wl["T"], wl["d"], len(wl["alg"])
@@ -168,6 +168,9 @@ def run_streamed(args, wl):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = float(world) * nb * A * T / float(t.item())
+    del z, y, flush
+    torch.cuda.empty_cache()
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -192,17 +195,19 @@ def run_streamed(args, wl):
                     "api": "engine.simulate_batch (oco_simulate_batch_host)"},
             "gpu_launches": args.steps * 2, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "sim_wide_tma_kernel<2,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
+                         "traffic": None, "kernel": "sim_wide_tma_kernel<64,16,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
                          "passes_over_input": passes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "result_check": {"mean_regret": float(reg.mean().item()), "max_regret": float(reg.max().item())},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and emit:
             v, cores, sample = cpu_stream_rate(wl, min(args.cpu_budget, 10.0))
             line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
-    if world > 1:
+        if emit:
+            print(json.dumps(line))
+    if world > 1 and init_dist:
         dist.destroy_process_group()
+    return line
 
 
 def run_reference(args, wl):
@@ -245,6 +250,7 @@ def main():
     ap.add_argument("--trials", type=int, default=0, help="sequences per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work (rank 0, N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the brief c5 / c4 measurements appended to the default c3 line")
     ap.add_argument("--comparator", default="linear", choices=["linear", "two_pass"], help="c4 only")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -340,7 +346,9 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64-pipe", "achieved": kernel_steps_per_s * alg_ops / 1e9, "peak": fp64_peak / 1e9,
                          "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak, "traffic": None,
-                         "kernel": "sweep_kernel<GPathStream,%d,%d>" % (d, 9 if A > 3 else (3 if A > 1 else 1)),
+                         "kernel": "sweep_kernel<GPathStream<%d>,%d,%d,%d>" % (
+                             d, d, int(any(f != 0 for f in wl["alg"])),
+                             (lambda n: 1 if n <= 1 else (4 if n <= 4 else 8))(sum(1 for f in wl["alg"] if f == 0))),
                          "algorithmic_ops_per_trajectory_step": alg_ops,
                          "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)"},
             "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
@@ -349,6 +357,34 @@ def main():
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_sweep_rate(wl, args.cpu_budget)
             line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    # the other BASELINE configurations, measured briefly in the same run (N = 1 default run only)
+    if world == 1 and args.workload == "c3" and not args.no_extras:
+        del flush
+        torch.cuda.empty_cache()
+        extras = {}
+        try:
+            w5 = dict(WORKLOADS["c5"]); w5["trials"] = 250_000
+            for _ in range(2):
+                engine.regret_sweep_device("gpath", w5["trials"], w5["T"], w5["d"], w5["alg"], w5["eta"])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                engine.regret_sweep_device("gpath", w5["trials"], w5["T"], w5["d"], w5["alg"], w5["eta"])
+            e1.record(); torch.cuda.synchronize()
+            r5 = 2 * w5["trials"] * w5["T"] / (e0.elapsed_time(e1) * 1e-3)
+            extras["c5_d5_ftrl_sweep"] = {"value": r5, "unit": "trajectory-steps/s", "trials": w5["trials"], "T": w5["T"],
+                                          "roofline": {"bound": "fp64-pipe", "achieved": r5 * 51 / 1e9, "peak": fp64_peak / 1e9,
+                                                       "unit": "Gop/s (non-fused fp64)", "frac": r5 * 51 / fp64_peak}}
+            sargs = argparse.Namespace(**vars(args)); sargs.steps, sargs.warmup = 3, 2
+            for mode in ("linear", "two_pass"):
+                sargs.comparator = mode
+                l4 = run_streamed(sargs, dict(WORKLOADS["c4"]), emit=False, init_dist=False)
+                extras["c4_d64_streamed_" + mode] = {k: l4[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "config")}
+        except Exception as ex:      # extras must never cost the headline number
+            extras["error"] = repr(ex)
+        line["other_workloads"] = extras
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -195,7 +195,9 @@ def run_streamed(args, wl, *, emit=True, init_dist=True):
                     "api": "engine.simulate_batch (oco_simulate_batch_host)"},
             "gpu_launches": args.steps * 2, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "sim_wide_tma_kernel<64,16,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
+                         "traffic": (lambda v: None if v is None else v * passes)(ncu_traffic("sim_wide_tma_kernel<64,16,double>", float(B) * A * T)),
+                         "traffic_note": "bytes per launch from the committed ncu capture (linear mode) x passes over the input",
+                         "kernel": "sim_wide_tma_kernel<64,16,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
                          "passes_over_input": passes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "result_check": {"mean_regret": float(reg.mean().item()), "max_regret": float(reg.max().item())},
@@ -204,7 +206,7 @@ def run_streamed(args, wl, *, emit=True, init_dist=True):
             v, cores, sample = cpu_stream_rate(wl, min(args.cpu_budget, 10.0))
             line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
         if emit:
-            print(json.dumps(line))
+            emit_line(line)
     if world > 1 and init_dist:
         dist.destroy_process_group()
     return line
@@ -217,6 +219,15 @@ def run_reference(args, wl):
         return
     from oracle import oracle as O
     A = len(wl["alg"]); cores = O.num_threads()
+    if wl.get("streamed"):      # pre-generated resident sequences, simulation only (what the streamed kernel does)
+        v, cores, sample = cpu_stream_rate(wl, max(5.0, min(60.0, 10.0 * args.steps)))
+        emit_line({"impl": "reference", "metric": "trajectory-steps/sec", "value": v, "unit": "trajectory-steps/s",
+                   "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                   "config": {"workload": wl["name"], "T": wl["T"], "d": wl["d"], "variants": A},
+                   "cpu_baseline": {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                   "e2e": {"value": v, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     n0 = max(cores, 8)
     t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"])
@@ -230,17 +241,47 @@ def run_reference(args, wl):
     dt = time.perf_counter() - t0
     val = args.steps * n * A * wl["T"] / dt
     sample = f"{n} trials/step x T={wl['T']} x A={A}, oracle port (C, OpenMP), generation included"
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": "trajectory-steps/sec", "value": val, "unit": "trajectory-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["name"], "trials_per_step": n, "T": wl["T"], "d": wl["d"], "variants": A},
         "cpu_baseline": {"value": val, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def ncu_traffic(kernel: str, units_per_launch: float):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled from the committed ncu capture
+    (profiles/r01_dram_traffic.json: bytes per trajectory-step of that kernel), or None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[kernel]
+        return rec["dram_bytes_per_trajectory_step"] * units_per_launch
+    except Exception:
+        return None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -331,6 +372,9 @@ def main():
         fp64_peak = engine.fp64_peak_ops(local)
         kernel_steps_per_s = B * A * T * args.steps / (ms * 1e-3)           # this GPU's kernel rate
         alg_ops = (9 * d + 6)
+        kname = "sweep_kernel<GPathStream<%d>,%d,%d,%d>" % (
+            d, d, int(any(f != 0 for f in wl["alg"])),
+            (lambda n: 1 if n <= 1 else (4 if n <= 4 else 8))(sum(1 for f in wl["alg"] if f == 0)))
         line = {
             "metric": "trajectory-steps/sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -345,10 +389,8 @@ def main():
             "gpu_launches": args.steps * 3 + (args.steps if world > 1 else 0),
             "clocks": clocks,
             "roofline": {"bound": "fp64-pipe", "achieved": kernel_steps_per_s * alg_ops / 1e9, "peak": fp64_peak / 1e9,
-                         "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak, "traffic": None,
-                         "kernel": "sweep_kernel<GPathStream<%d>,%d,%d,%d>" % (
-                             d, d, int(any(f != 0 for f in wl["alg"])),
-                             (lambda n: 1 if n <= 1 else (4 if n <= 4 else 8))(sum(1 for f in wl["alg"] if f == 0))),
+                         "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak,
+                         "traffic": ncu_traffic(kname, float(B) * A * T), "kernel": kname,
                          "algorithmic_ops_per_trajectory_step": alg_ops,
                          "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)"},
             "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
@@ -385,7 +427,7 @@ def main():
             extras["error"] = repr(ex)
         line["other_workloads"] = extras
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 

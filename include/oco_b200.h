@@ -80,12 +80,15 @@ OCO_API int oco_device_count(int* count);
  * (exact_ftl.run_ftrl(..., comparator_action=...)); NULL = the reference's FTL action of the
  * final theta (d <= 8 only).  Outputs ([B*A] unless noted, any may be NULL): regret =
  * cum_loss - comp_loss, cum_loss, comp_loss, theta_final [B*A*d], x_last [B*A*d] (the action
- * played at the last round, RunResult.x_last; d <= 8), x_trace [B*A*T*d] (all played x_t; d <= 8). */
-OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+ * played at the last round, RunResult.x_last; d <= 8), x_trace [B*A*T*d] (all played x_t; d <= 8).
+ * compute_dtype: OCO_F64 = the numba path fast_algorithms.py (float64 state, the default and the
+ * parity target); OCO_F32 = the NumPy path algorithms.py:28-54 (float32 theta / x, float64 loss
+ * accumulator; needs in_dtype == OCO_F32, d <= 8, no comparator / x_trace; tolerance 1e-5). */
+OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int compute_dtype, int64_t B, int64_t T, int d,
                        const int* alg_flag, const double* eta0, int A, const double* comparator,
                        double* regret, double* cum_loss, double* comp_loss,
                        double* theta_final, double* x_last, double* x_trace, int comparator_mode, void* stream);
-OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int compute_dtype, int64_t B, int64_t T, int d,
                             const int* alg_flag, const double* eta0, int A, const double* comparator,
                             double* regret, double* cum_loss, double* comp_loss,
                             double* theta_final, double* x_last, double* x_trace, int comparator_mode, int device);

@@ -21,8 +21,8 @@ SIGNATURES = {
     "oco_last_error": ([], C.c_char_p),
     "oco_abi_version": ([], _i),
     "oco_device_count": ([C.POINTER(_i)], _i),
-    "oco_simulate_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
-    "oco_simulate_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
+    "oco_simulate_batch": ([_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "oco_simulate_batch_host": ([_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
     "oco_exact_ftl_prefix_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "oco_replay_actions_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i], _i),
     "oco_exact_ftl_prefix_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i], _i),

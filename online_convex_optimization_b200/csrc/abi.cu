@@ -124,7 +124,7 @@ OCO_API int oco_device_count(int* count) {
 }
 
 // ---------------------------------------------------------------------------------- simulate
-OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int compute_dtype, int64_t B, int64_t T, int d,
                        const int* alg_flag, const double* eta0, int A, const double* comparator,
                        double* regret, double* cum_loss, double* comp_loss,
                        double* theta_final, double* x_last, double* x_trace, int comparator_mode, void* stream) {
@@ -134,6 +134,9 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64
         return fail(OCO_ERR_VALUE, "x_trace / x_last / comparator are available for d <= %d only", kMaxSmallD);
     if (comparator_mode != OCO_COMPARATOR_TWO_PASS && comparator_mode != OCO_COMPARATOR_LINEAR)
         return fail(OCO_ERR_VALUE, "unknown comparator_mode %d", comparator_mode);
+    if (compute_dtype != OCO_F32 && compute_dtype != OCO_F64) return fail(OCO_ERR_VALUE, "compute_dtype must be OCO_F32 or OCO_F64");
+    if (compute_dtype == OCO_F32 && (in_dtype != OCO_F32 || d > kMaxSmallD || comparator || x_trace))
+        return fail(OCO_ERR_VALUE, "float32 compute mode needs float32 inputs, d <= %d, no comparator / x_trace", kMaxSmallD);
     Variants v; Etas e;
     if (int rc = make_variants(alg_flag, eta0, A, v, e)) return rc;
     if (B == 0) return OCO_OK;
@@ -141,7 +144,9 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64
     DevBuf tab;
     CU(tab.alloc(sizeof(double) * (size_t)(T * A), st));
     CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
-    if (d <= kMaxSmallD)
+    if (compute_dtype == OCO_F32)
+        CU(launch_sim_stream_f32(z, y, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, x_last, st));
+    else if (d <= kMaxSmallD)
         CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), comparator, regret, cum_loss, comp_loss,
                              theta_final, x_last, x_trace, st));
     else if (wide_tma_eligible(z, y, in_dtype == OCO_F32, T, d))
@@ -151,7 +156,7 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int64
     return OCO_OK;
 }
 
-OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
+OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, int compute_dtype, int64_t B, int64_t T, int d,
                             const int* alg_flag, const double* eta0, int A, const double* comparator,
                             double* regret, double* cum_loss, double* comp_loss,
                             double* theta_final, double* x_last, double* x_trace, int comparator_mode, int device) {
@@ -182,7 +187,7 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
         CU(cudaMemcpyAsync(zd[i].p, (const char*)z + (size_t)b0 * T * d * es, (size_t)nb * T * d * es, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(yd[i].p, (const char*)y + (size_t)b0 * T * es, (size_t)nb * T * es, cudaMemcpyHostToDevice, s));
         if (comparator) CU(cudaMemcpyAsync(qd[i].p, comparator + b0 * d, (size_t)nb * d * 8, cudaMemcpyHostToDevice, s));
-        if (int rc = oco_simulate_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, alg_flag, eta0, A,
+        if (int rc = oco_simulate_batch(zd[i].p, yd[i].p, in_dtype, compute_dtype, nb, T, d, alg_flag, eta0, A,
                                         comparator ? qd[i].as<double>() : nullptr,
                                         rd[i].as<double>(), cd[i].as<double>(), pd[i].as<double>(),
                                         theta_final ? td[i].as<double>() : nullptr, x_last ? ld[i].as<double>() : nullptr,

@@ -103,6 +103,111 @@ __global__ void __launch_bounds__(kStreamBlock) sim_stream_kernel(const StreamAr
     }
 }
 
+// ------------------------------------------------------------------ float32 compute mode
+// Mirror of the reference's NumPy implementation algorithms.py:28-54 (float32 state): theta and x
+// are float32; np.dot / np.linalg.norm on short float32 vectors go through OpenBLAS sdot, which
+// forms float products and accumulates them in a double before rounding to float (probe,
+// DESIGN.md section 2); Python-float scalars multiply float32 arrays as float32 (NumPy 2 weak
+// promotion); the cumulative loss is a Python float (double).  The comparator loss is a float32
+// BLAS matvec + pairwise float32 sum in the reference; here its float32 terms are accumulated in
+// double -- the mode's contract is 1e-5 relative (north_star), not bit parity.
+template <int D>
+__device__ __forceinline__ float sdot_like(const float (&a)[D], const float (&b)[D]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) acc = acc + (double)(a[j] * b[j]);
+    return (float)acc;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kStreamBlock) sim_stream_f32_kernel(const StreamArgs p) {
+    const int64_t b = (int64_t)blockIdx.x * kStreamBlock + threadIdx.x;
+    if (b >= p.B) return;
+    const int A = p.v.A, a = blockIdx.y;
+    const bool ftrl = p.v.alg_flag[a] == 0;
+    const float* __restrict__ zb = (const float*)p.z + b * p.T * D;
+    const float* __restrict__ yb = (const float*)p.y + b * p.T;
+    float th[D], x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { th[j] = 0.0f; x[j] = 0.0f; }
+    double cum = 0.0;
+    auto act_ftl = [&]() {                                   // algorithms.py:13-15
+        const float n = sqrtf(sdot_like<D>(th, th));
+        const float sc = -(1.0f / n);
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = (n == 0.0f) ? 0.0f : sc * th[j];
+    };
+    for (int64_t t = 0; t < p.T; ++t) {
+        if (ftrl) {                                          // algorithms.py:17-21
+            const float sc = (float)__ldg(p.tab + t * A + a);
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = sc * th[j];
+            const float n = sqrtf(sdot_like<D>(x, x));
+            if (n > 1.0f) {
+                const float inv = 1.0f / n;
+#pragma unroll
+                for (int j = 0; j < D; ++j) x[j] = x[j] * inv;
+            }
+        } else {
+            act_ftl();
+        }
+        float z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = zb[t * D + j];
+        const double q = (double)sdot_like<D>(z, x);         // float(np.dot(z[t], x_t))
+        const double y = (double)yb[t];
+        const double df = q - y;
+        cum = cum + 0.5 * fabs(df);
+        const float g = df > 0.0 ? 0.5f : (df < 0.0 ? -0.5f : 0.0f);
+#pragma unroll
+        for (int j = 0; j < D; ++j) th[j] = th[j] + g * z[j];
+        if (p.x_last && t == p.T - 1) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) p.x_last[(b * A + a) * D + j] = (double)x[j];
+        }
+    }
+    act_ftl();
+    double comp = 0.0;
+    for (int64_t t = 0; t < p.T; ++t) {
+        float z[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = zb[t * D + j];
+        const float r = sdot_like<D>(z, x) - yb[t];
+        comp = comp + (double)(0.5f * fabsf(r));
+    }
+    const int64_t o = b * A + a;
+    if (p.regret) p.regret[o] = cum - comp;
+    if (p.cum) p.cum[o] = cum;
+    if (p.comp) p.comp[o] = comp;
+    if (p.theta_final) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) p.theta_final[o * D + j] = (double)th[j];
+    }
+}
+
+cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64_t T, int d,
+                                  const Variants& v, const double* scale_tab,
+                                  double* regret, double* cum, double* comp, double* theta_final, double* x_last,
+                                  cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    StreamArgs a;
+    a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.comparator = nullptr;
+    a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_last = x_last; a.x_trace = nullptr; a.v = v;
+    const dim3 grid((unsigned)((B + kStreamBlock - 1) / kStreamBlock), (unsigned)v.A);
+    switch (d) {
+    case 1: sim_stream_f32_kernel<1><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 2: sim_stream_f32_kernel<2><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 3: sim_stream_f32_kernel<3><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 4: sim_stream_f32_kernel<4><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 5: sim_stream_f32_kernel<5><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 6: sim_stream_f32_kernel<6><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 7: sim_stream_f32_kernel<7><<<grid, kStreamBlock, 0, st>>>(a); break;
+    case 8: sim_stream_f32_kernel<8><<<grid, kStreamBlock, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 template <int D, typename TIN>
 static cudaError_t launch_stream_d(const StreamArgs& a, cudaStream_t st) {
     const int A = a.v.A;

@@ -65,6 +65,11 @@ cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t 
                               const Variants& v, const double* scale_tab, const double* comparator,
                               double* regret, double* cum, double* comp, double* theta_final, double* x_last,
                               double* x_trace, cudaStream_t st);
+// float32 compute mode (algorithms.py semantics), float32 inputs, d <= 8
+cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64_t T, int d,
+                                  const Variants& v, const double* scale_tab,
+                                  double* regret, double* cum, double* comp, double* theta_final, double* x_last,
+                                  cudaStream_t st);
 // exact FTL prefix actions + replay in the linear regime (||z||<=1, y=+-1), d <= 8
 cudaError_t launch_exact_ftl_linear(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                                     double* actions, double* cum, double* comp, double* regret, int* status,

@@ -87,8 +87,12 @@ __device__ __forceinline__ void project_unit_ball(double (&x)[D], double n2, uns
     }
 }
 
+// resident CTAs per SM the register allocator must allow (more warps hide the serial RNG / fp64 chains)
+#ifndef OCO_SWEEP_MIN_BLOCKS
+#define OCO_SWEEP_MIN_BLOCKS 5
+#endif
 template <class Stream, int D, int NFTL, int NF>
-__global__ void __launch_bounds__(kSweepBlock) sweep_kernel(const SweepArgs p) {
+__global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 4)) sweep_kernel(const SweepArgs p) {
     __shared__ ZigTables tb;
     __shared__ double red[kSweepBlock / 32][3];
     zig_tables_load(tb);

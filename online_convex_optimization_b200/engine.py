@@ -65,10 +65,11 @@ def _keys(keys, B):
 
 # ----------------------------------------------------------------------------- host API
 def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = False,
-                   comparator: str = "two_pass", comparator_action=None, device: int = 0):
+                   comparator: str = "two_pass", comparator_action=None, compute: str = "f64", device: int = 0):
     """Batched fast_algorithms.simulate_alg: z (B,T,d), y (B,T) -> regret (B,A).
     full=True returns a dict with cum_loss, comp_loss, theta (B,A,d), x_last (B,A,d; d <= 8)
-    [and x_trace (B,A,T,d)].  comparator_action (B,d): fixed comparator (exact_ftl.run_ftrl)."""
+    [and x_trace (B,A,T,d)].  comparator_action (B,d): fixed comparator (exact_ftl.run_ftrl).
+    compute="f32": the float32-state semantics of the reference's algorithms.py (float32 inputs)."""
     z, y, dt = _prep_zy(z, y)
     B, T, d = z.shape
     af, et = _variants(alg_flags, eta0s)
@@ -85,7 +86,8 @@ def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = 
         if ca.shape != (B, d):
             raise ValueError(f"comparator_action must have shape ({B}, {d})")
     mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
-    _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(af), _vp(et), A, _vp(ca),
+    cdt = {"f64": OCO_F64, "f32": OCO_F32}[compute]
+    _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, cdt, B, T, d, _vp(af), _vp(et), A, _vp(ca),
                                                    _vp(reg), _vp(cum), _vp(comp), _vp(th), _vp(xl), _vp(xt), mode, device))
     if not full and not trace:
         return reg
@@ -220,7 +222,7 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
     th = torch.empty((B, A, d), dtype=torch.float64, device=z.device) if full else None
     mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
     with torch.cuda.device(z.device):
-        _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
+        _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64, OCO_F64,
                                                   B, T, d, _vp(af), _vp(et), A, None, _dptr(reg), _dptr(cum), _dptr(comp),
                                                   _dptr(th), None, None, mode, _stream_ptr(torch)))
     if not full:

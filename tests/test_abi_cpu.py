@@ -60,9 +60,9 @@ def test_argument_validation_is_value_error():
         engine.gen_sequences("gpath", 2, 4, 5, keys=np.zeros((3, 2)))
     lib = _lib.load()
     # straight through the C ABI: bad dtype / negative sizes / NULL pointers are OCO_ERR_VALUE
-    rc = lib.oco_simulate_batch(None, None, 7, 1, 1, 1, None, None, 1, None, None, None, None, None, None, None, 0, None)
+    rc = lib.oco_simulate_batch(None, None, 7, 1, 1, 1, 1, None, None, 1, None, None, None, None, None, None, None, 0, None)
     assert rc == _lib.OCO_ERR_VALUE and b"dtype" in lib.oco_last_error()
-    rc = lib.oco_simulate_batch(None, None, 1, -1, 1, 1, None, None, 1, None, None, None, None, None, None, None, 0, None)
+    rc = lib.oco_simulate_batch(None, None, 1, 1, -1, 1, 1, None, None, 1, None, None, None, None, None, None, None, 0, None)
     assert rc == _lib.OCO_ERR_VALUE
     af = (ctypes.c_int * 1)(0)
     et = (ctypes.c_double * 1)(1.0)

@@ -259,3 +259,26 @@ def test_full_size_properties(eng):
     assert (bits(a[:4]) == bits(O.regret_sweep(0, T, 0, 4, 1, [1, 0, 0], [R2, R2, 0.5]))).all()
     z, y = eng.gen_sequences("flip", 1, T, 5)
     assert eng.simulate_batch(z, y, [1], [R2])[0, 0] == T / 4
+
+
+# ------------------------------------------------------------------ float32 compute mode (algorithms.py)
+def test_float32_mode_matches_numpy_reference(eng, golden_sim):
+    """The optional fp32 mode (algorithms.py semantics): 1e-5 relative to the reference's float32 results."""
+    from online_convex_optimization_b200 import algorithms as alg32
+    n = 0
+    for case in golden_sim["cases"]:
+        if "f32_alg0" not in case["results"]:
+            continue
+        z, y = make_sequence(case["spec"])
+        z32, y32 = np.asarray(z, dtype=np.float32), np.asarray(y, dtype=np.float32)
+        for flag in (0, 1):
+            want = hexf(case["results"][f"f32_alg{flag}"])
+            got = alg32.simulate_alg(z32, y32, flag, R2)
+            assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (case["name"], flag, got, want)
+            n += 1
+    assert n >= 30
+    with pytest.raises(ValueError):
+        eng.simulate_batch(np.zeros((1, 4, 2)), np.zeros((1, 4)), [0], [1.0], compute="f32")   # needs float32 inputs
+    g = alg32.empirical_worst_case_thresholds(np.array([100]), runs=50, base_seed=0)
+    g64 = O.empirical_worst_case_thresholds(np.array([100]), runs=50, base_seed=0)
+    assert abs(g[100] - g64[100]) <= 1e-5 * g64[100]

@@ -206,7 +206,7 @@ def _dptr(t) -> C.c_void_p:
     return C.c_void_p(None if t is None else t.data_ptr())
 
 
-def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, comparator: str = "two_pass"):
+def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, comparator: str = "two_pass", compute: str = "f64"):
     """z (B,T,d), y (B,T): contiguous CUDA tensors (float32 or float64).  Returns CUDA tensors."""
     torch = _torch()
     if z.dtype != y.dtype or z.dtype not in (torch.float32, torch.float64):
@@ -222,8 +222,8 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
     th = torch.empty((B, A, d), dtype=torch.float64, device=z.device) if full else None
     mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
     with torch.cuda.device(z.device):
-        _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64, OCO_F64,
-                                                  B, T, d, _vp(af), _vp(et), A, None, _dptr(reg), _dptr(cum), _dptr(comp),
+        _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
+                                                  {"f64": OCO_F64, "f32": OCO_F32}[compute], B, T, d, _vp(af), _vp(et), A, None, _dptr(reg), _dptr(cum), _dptr(comp),
                                                   _dptr(th), None, None, mode, _stream_ptr(torch)))
     if not full:
         return reg

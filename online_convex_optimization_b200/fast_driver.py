@@ -50,7 +50,8 @@ def _sem(x: FloatArray) -> float:
     return float(np.std(x, ddof=1) / math.sqrt(n))
 
 
-def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicates: int, base_seed: int) -> np.ndarray:
+def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicates: int, base_seed: int,
+                   compute: str = "f64") -> np.ndarray:
     """Per-sequence regrets, shape (runs, replicates, 4) in ALGO_KEYS order, for one horizon."""
     samplers = [stream_builder(run_seed=base_seed + 2025 * (run + 1)) for run in range(runs)]
     spec = getattr(samplers[0], "spec", None)
@@ -66,7 +67,7 @@ def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicat
                             dtype=np.uint64)
         z, y = engine.gen_sequences_device(fam, B, T, d, keys=keys, p_flip=spec["p"], block_len=spec.get("block_len", 20),
                                            dtype=torch.float32)
-        alg = engine.simulate_batch_device(z, y, [0, 1], [SQRT2, SQRT2])
+        alg = engine.simulate_batch_device(z, y, [0, 1], [SQRT2, SQRT2], compute=compute)
         smart, _ = engine.smart_batch_device(z, y, thresholds, [SQRT2, SQRT2])
         out = torch.cat([alg, smart], dim=1).cpu().numpy()
     else:
@@ -78,7 +79,7 @@ def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicat
                 zs.append(z)
                 ys.append(y)
         z, y = np.stack(zs), np.stack(ys)
-        alg = engine.simulate_batch(z, y, [0, 1], [SQRT2, SQRT2])
+        alg = engine.simulate_batch(z, y, [0, 1], [SQRT2, SQRT2], compute=compute)
         smart, _ = engine.smart_batch(z, y, thresholds, [SQRT2, SQRT2])
         out = np.concatenate([alg, smart], axis=1)
     return out.reshape(runs, replicates, 4)
@@ -93,12 +94,14 @@ def evaluate_stream_with_stats(
     replicates: int = 1,
     base_seed: int = 0,
     stream_name: str = "",
+    compute: str = "f64",
 ) -> Stats:
-    """fast_driver.py:71-127 -- mean regret and 95 % CI per algorithm at each T."""
+    """fast_driver.py:71-127 -- mean regret and 95 % CI per algorithm at each T.
+    compute="f32" plays FTRL / FTL with the float32-state semantics of algorithms.py (driver.py twin)."""
     by_T = {k: [] for k in ALGO_KEYS}
     for T in T_grid:
         T_int = int(T)
-        reg = _regrets_for_T(stream_builder, T_int, float(g_emp[T_int]), runs, replicates, base_seed)
+        reg = _regrets_for_T(stream_builder, T_int, float(g_emp[T_int]), runs, replicates, base_seed, compute)
         for ki, k in enumerate(ALGO_KEYS):
             # fast_driver.py:113-114: per run, float(np.mean(list of replicate regrets))
             by_T[k].append([float(np.mean([float(v) for v in reg[run, :, ki]])) for run in range(runs)])

@@ -149,3 +149,16 @@ def test_exact_driver_twin_small():
     fast = fd.evaluate_stream_with_stats(sg.CASES["Random i.i.d. (separable)"], cfg.T_grid, {100: 1.0, 200: 1.0},
                                          runs=3, replicates=2)
     assert np.allclose(st["FTL (exact)"][0], fast["FTL"][0], rtol=1e-9, atol=1e-9)
+
+
+def test_driver_twin_float32_columns(golden_stats):
+    """driver.py twin (float32-state algorithms): within 1e-5 of the float64 golden statistics."""
+    from online_convex_optimization_b200 import driver as dr
+    from online_convex_optimization_b200 import sequence_generation as sg
+    g_emp = {int(k): hexf(v) for k, v in golden_stats["g_emp_runs1000"].items()}
+    rec = golden_stats["stats_small"]["Massart noise 10%"]
+    got = dr.evaluate_stream_with_stats(sg.CASES["Massart noise 10%"], np.array([100, 200, 300]), g_emp, runs=rec["runs"],
+                                        replicates=rec["replicates"], base_seed=0)
+    for k in ("FTRL", "FTL"):
+        want = np.array([hexf(v) for v in rec["stats"][k][0]])
+        assert np.all(np.abs(got[k][0] - want) <= 1e-5 * np.maximum(1.0, np.abs(want)))

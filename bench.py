@@ -403,6 +403,7 @@ def main():
     if world == 1 and args.workload == "c3" and not args.no_extras:
         del flush
         torch.cuda.empty_cache()
+        engine.release_scratch(local)
         extras = {}
         try:
             w5 = dict(WORKLOADS["c5"]); w5["trials"] = 250_000
@@ -418,6 +419,7 @@ def main():
             extras["c5_d5_ftrl_sweep"] = {"value": r5, "unit": "trajectory-steps/s", "trials": w5["trials"], "T": w5["T"],
                                           "roofline": {"bound": "fp64-pipe", "achieved": r5 * 51 / 1e9, "peak": fp64_peak / 1e9,
                                                        "unit": "Gop/s (non-fused fp64)", "frac": r5 * 51 / fp64_peak}}
+            engine.release_scratch(local)
             sargs = argparse.Namespace(**vars(args)); sargs.steps, sargs.warmup = 3, 2
             for mode in ("linear", "two_pass"):
                 sargs.comparator = mode

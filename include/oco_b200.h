@@ -160,6 +160,10 @@ OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int
  * n_skip normals are consumed first.  out: HOST buffer of n 8-byte items. */
 OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device);
 
+/* ---- scratch (the sweep kernel's row slab, scale tables) is allocated stream-ordered and kept cached
+ * in the device's default memory pool between calls; this returns it to the driver. */
+OCO_API int oco_release_scratch(int device);
+
 /* ---- roofline denominator for the generated-on-device kernels: measured issue rate of
  * independent non-fused fp64 multiplies and adds (ops / second) on `device`. */
 OCO_API int oco_fp64_peak_probe_host(int device, double* ops_per_sec);

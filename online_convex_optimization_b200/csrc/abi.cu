@@ -489,6 +489,15 @@ OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int
     return OCO_OK;
 }
 
+OCO_API int oco_release_scratch(int device) {
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    CU(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    CU(cudaMemPoolTrimTo(pool, 0));
+    return OCO_OK;
+}
+
 OCO_API int oco_fp64_peak_probe_host(int device, double* ops_per_sec) {
     if (!ops_per_sec) return fail(OCO_ERR_VALUE, "ops_per_sec must not be NULL");
     DeviceGuard g; if (int rc = g.set(device)) return rc;

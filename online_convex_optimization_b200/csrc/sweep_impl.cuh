@@ -300,7 +300,16 @@ static cudaError_t launch_sweep_cfg(SweepArgs a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const int64_t chunks = (a.B + kSweepBlock - 1) / kSweepBlock;
     a.n_items = chunks * a.plan.groups;
-    const int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
+    int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
+    {   // never ask for more than ~70 % of the free device memory: fewer resident CTAs, same result
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t per_cta = (size_t)a.T * D * kSweepBlock * sizeof(E) + (size_t)((a.T + 31) / 32) * kSweepBlock * 4 + 1;
+            const int64_t fit = (int64_t)((free_b / 10) * 7 / per_cta);
+            if (fit < 1) return cudaErrorMemoryAllocation;
+            grid = std::min<int64_t>(grid, fit);
+        }
+    }
     const size_t zbytes = (size_t)grid * a.T * D * kSweepBlock * sizeof(E);
     const size_t ybytes = (size_t)grid * ((a.T + 31) / 32) * kSweepBlock * sizeof(uint32_t);
     void* slab = nullptr;

@@ -183,6 +183,11 @@ def rng_probe(what: int, key, n: int, n_skip: int = 0, device: int = 0):
     return out
 
 
+def release_scratch(device: int = 0) -> None:
+    """Return the library's cached scratch memory (sweep slab, tables) to the driver."""
+    _lib.check(_lib.load().oco_release_scratch(device))
+
+
 def fp64_peak_ops(device: int = 0) -> float:
     """Measured issue rate (ops/s) of independent, non-fused fp64 multiplies and adds."""
     v = C.c_double(0.0)

@@ -1,14 +1,13 @@
-// kernels_seeded.cu -- sequences generated on the device from their numpy stream keys.
+// kernels_seeded.cu -- host-side glue and small kernels around the seeded families.
 //
-//  sweep_kernel<Stream, D, AV>   generate + simulate + compare, fused: one thread per
-//      sequence keeps the RNG cursors, AV trajectories' theta / cumulative loss and the
-//      comparator accumulators in registers; the sequence is regenerated for the
-//      comparator pass (fast_algorithms.py:113-114 needs the FINAL theta) instead of
-//      being stored, so the kernel touches HBM only for its 8*A-byte result per sequence.
-//      Bound: fp64 pipe / issue slots, never HBM.
-//  fill_kernel<Stream, D, TOUT>  write the sequences to HBM (z[B][T][d], y[B][T]) for the
-//      streamed kernels (BASELINE config 4) and for callers that want the arrays.
-//  stats_finalize_kernel        fixed-order reduction of the per-block (max, sum, sumsq).
+//  make_sweep_plan / launch_sweep   canonical variant layout + dispatch of the fused sweep kernel
+//      (sweep_impl.cuh; instantiated in kernels_sweep_gpath.cu / kernels_sweep_iid.cu)
+//  fill_kernel<Stream, D, TOUT>     write the sequences to HBM in the reference layout
+//      (z[B][T][d], y[B][T]) for the streamed kernels (BASELINE config 4) and for callers that
+//      want the arrays; rows first, then labels, in numpy's draw order
+//  sweep_table_kernel / ftrl_scale_table_kernel   -(eta0/sqrt(t)) tables (IEEE sqrt and divide)
+//  stats_finalize_kernel            fixed-order reduction of the per-chunk (max, sum, sumsq)
+//  rng_probe_kernel                 known-answer probes of the device generator
 #include "sweep_impl.cuh"
 
 namespace oco {

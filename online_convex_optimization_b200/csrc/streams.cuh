@@ -1,11 +1,11 @@
-// streams.cuh -- on-device sequence families: one CUDA thread regenerates exactly the
-// (z_t, y_t) rows the reference's numpy generators produce for one stream key.
+// streams.cuh -- on-device sequence families: one CUDA thread produces exactly the (z_t, y_t) rows
+// the reference's numpy generators produce for one stream key.
 //   GPathStream  fast_algorithms.py:231-239      float64 rows, Rademacher labels via choice()
 //   IidStream    sequence_generation.py:54-90    float32 rows, labels sign(z.u), optional Massart flips
-// Both keep a "normal cursor" and a second cursor positioned after all T*d normals
-// (numpy draws every normal first, then the labels / flip uniforms from the same
-// stream), found once per stream by zig_skip(); rewind() restarts both for the
-// comparator pass so that no sequence ever has to be stored.
+// numpy draws every normal of a sequence first and the labels / flip uniforms afterwards from the
+// same stream, and the ziggurat consumes a data-dependent number of raw draws, so the label
+// cursor is only known once all T*d normals have been generated: the stream protocol below
+// (row / begin_labels / label) generates each row exactly once, in numpy's order.
 #pragma once
 #include "oco_device.cuh"
 #include "rng_numpy.cuh"

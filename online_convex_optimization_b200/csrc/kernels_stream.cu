@@ -208,10 +208,230 @@ cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ cp.async-staged version
+// Same arithmetic as sim_stream_kernel, different data path.  In the reference layout a thread's
+// rows are contiguous but neighbouring lanes are T*D*sizeof(TIN) bytes apart, so direct loads touch
+// 32 different 128-byte lines per warp instruction and the kernel is L1/LSU-bound (~1 TB/s).
+// Here every warp stages, for its 32 sequences, a tile of kAT rows (+ labels) into shared memory
+// with 16-byte cp.async (LDGSTS): the copy loop walks the 32 contiguous per-sequence chunks piece
+// by piece, so each warp instruction moves 512 B in 3-4 fully used segments.  Two tiles per warp
+// are in flight (double buffer, cp.async.wait_group 1); a sequence's record is padded to an odd
+// number of 16-byte units so that the consumer's 128-bit LDS are bank-conflict free.  Warps
+// synchronise only with __syncwarp.
+constexpr int kAT = 4;          // rows per tile
+constexpr int kAWarps = 4;      // warps per CTA
+
+template <int D, typename TIN>
+struct AsyncTile {
+    static constexpr int ES = sizeof(TIN);
+    static constexpr int ZB = kAT * D * ES;                       // z bytes per sequence per tile
+    static constexpr int YB = kAT * ES;                           // y bytes
+    static constexpr int NP = (ZB + YB) / 16;                     // 16-byte pieces per sequence
+    static constexpr int RECP = (NP % 2 == 0) ? NP + 1 : NP;      // padded record, odd number of pieces
+    static constexpr int REC = RECP * 16;
+    static constexpr int STAGE = 32 * REC;                        // bytes per warp per stage
+    // rows per register group: smallest R | kAT with R*D*ES a multiple of 16
+    static constexpr int RG = ((D * ES) % 16 == 0) ? 1 : (((2 * D * ES) % 16 == 0) ? 2 : 4);
+    static constexpr int GV = RG * D * ES / 16;                   // uint4 per row group
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D, int AV, typename TIN>
+__global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_async_kernel(const StreamArgs p) {
+    typedef AsyncTile<D, TIN> L;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b0 = ((int64_t)blockIdx.x * kAWarps + wib) * 32;        // first sequence of this warp
+    if (b0 >= p.B) return;
+    const int64_t b = b0 + lane;
+    const bool active = b < p.B;
+    const int nseq = (int)((p.B - b0) < 32 ? (p.B - b0) : 32);
+    const int A = p.v.A;
+    const int v0 = blockIdx.y * AV;
+    const int nv = min(AV, A - v0);
+    const int64_t T = p.T;
+    const unsigned char* __restrict__ zw = (const unsigned char*)p.z + b0 * T * D * L::ES;    // warp bases
+    const unsigned char* __restrict__ yw = (const unsigned char*)p.y + b0 * T * L::ES;
+    unsigned char* wsm = smem_raw + (size_t)wib * 2 * L::STAGE;
+    const int ntiles = (int)(T / kAT);
+
+    auto stage_tile = [&](int tile, int st) {
+        unsigned char* dst = wsm + st * L::STAGE;
+        const int total = nseq * L::NP;
+        for (int pidx = lane; pidx < total; pidx += 32) {
+            const int s = pidx / L::NP, off = pidx - s * L::NP;
+            const unsigned char* src = (off < L::ZB / 16)
+                ? zw + ((int64_t)s * T + (int64_t)tile * kAT) * D * L::ES + off * 16
+                : yw + ((int64_t)s * T + (int64_t)tile * kAT) * L::ES + (off - L::ZB / 16) * 16;
+            cp_async16(dst + s * L::REC + off * 16, src);
+        }
+        cp_async_commit();
+    };
+
+    // trajectory state: theta and S = sum |q - y| (cum_loss = 0.5*S exactly, see sweep_impl.cuh)
+    double th[AV][D], S[AV], act[AV][D], C[AV];
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+        S[v] = 0.0; C[v] = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) th[v][j] = 0.0;
+    }
+    const unsigned wmask = __ballot_sync(0xffffffffu, active);
+
+    // one round; PASS 0 = play (fast_algorithms.py:99-111), PASS 1 = comparator (fast_algorithms.py:69-76)
+    auto row_step = [&](int pass, int64_t t, const double (&z)[D], double y) {
+        if (pass == 0) {
+            double hz[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) hz[j] = 0.5 * z[j];
+            const double* trow = p.tab + t * A + v0;
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                if (v < nv) {
+                    double x[D];
+                    if (p.v.alg_flag[v0 + v] == 0) {                 // fast_algorithms.py:52-66
+                        const double sc = __ldg(trow + v);
+#pragma unroll
+                        for (int j = 0; j < D; ++j) x[j] = sc * th[v][j];
+                        double n2 = x[0] * x[0];
+#pragma unroll
+                        for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                        project_unit_ball<D>(x, n2, wmask);
+                    } else {
+                        ftl_action<D>(th[v], x);                      // fast_algorithms.py:37-49
+                    }
+                    if (p.x_trace) {
+                        double* xo = p.x_trace + ((b * A + v0 + v) * T + t) * D;
+#pragma unroll
+                        for (int j = 0; j < D; ++j) xo[j] = x[j];
+                    }
+                    if (p.x_last && t == T - 1) {
+                        double* xo = p.x_last + (b * A + v0 + v) * D;
+#pragma unroll
+                        for (int j = 0; j < D; ++j) xo[j] = x[j];
+                    }
+                    const double df = dot_seq<D>(z, x) - y;
+                    S[v] = S[v] + fabs(df);
+                    grad_step<D>(th[v], hz, df);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < AV; ++v)
+                if (v < nv) C[v] = C[v] + fabs(dot_seq<D>(z, act[v]) - y);
+        }
+    };
+
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                if (p.comparator && active) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) act[v][j] = p.comparator[b * D + j];
+                } else {
+                    ftl_action<D>(th[v], act[v]);
+                }
+            }
+        }
+        if (ntiles > 0) stage_tile(0, 0);
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int st = tile & 1;
+            if (tile + 1 < ntiles) { stage_tile(tile + 1, st ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
+            if (active) {
+                const unsigned char* rec = wsm + st * L::STAGE + lane * L::REC;
+                TIN yv[kAT];
+                {
+                    uint4 ybuf[(L::YB + 15) / 16];
+#pragma unroll
+                    for (int i = 0; i < L::YB / 16; ++i) ybuf[i] = *reinterpret_cast<const uint4*>(rec + L::ZB + i * 16);
+                    const TIN* ye = reinterpret_cast<const TIN*>(ybuf);
+#pragma unroll
+                    for (int r = 0; r < kAT; ++r) yv[r] = ye[r];
+                }
+#pragma unroll
+                for (int g = 0; g < kAT / L::RG; ++g) {
+                    uint4 zbuf[L::GV];
+#pragma unroll
+                    for (int i = 0; i < L::GV; ++i) zbuf[i] = *reinterpret_cast<const uint4*>(rec + (g * L::GV + i) * 16);
+                    const TIN* ze = reinterpret_cast<const TIN*>(zbuf);
+#pragma unroll
+                    for (int r = 0; r < L::RG; ++r) {
+                        double z[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) z[j] = (double)ze[r * D + j];
+                        row_step(pass, (int64_t)tile * kAT + g * L::RG + r, z, (double)yv[g * L::RG + r]);
+                    }
+                }
+            }
+            __syncwarp();                                        // stage st may be overwritten by the next prefetch
+        }
+        if (active) {
+            const TIN* zb = reinterpret_cast<const TIN*>(zw) + (int64_t)lane * T * D;
+            const TIN* yb = reinterpret_cast<const TIN*>(yw) + (int64_t)lane * T;
+            for (int64_t t = (int64_t)ntiles * kAT; t < T; ++t) {      // ragged tail: direct loads
+                double z[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = (double)zb[t * D + j];
+                row_step(pass, t, z, (double)yb[t]);
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+        if (v < nv) {
+            const int64_t o = b * A + v0 + v;
+            const double cum = 0.5 * S[v], comp = 0.5 * C[v];
+            if (p.regret) p.regret[o] = cum - comp;
+            if (p.cum) p.cum[o] = cum;
+            if (p.comp) p.comp[o] = comp;
+            if (p.theta_final) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) p.theta_final[o * D + j] = th[v][j];
+            }
+        }
+    }
+}
+
+// every 16-byte piece must be 16-byte aligned in global memory
+template <int D, typename TIN>
+static bool async_eligible(const StreamArgs& a) {
+    const size_t es = sizeof(TIN);
+    return ((uintptr_t)a.z % 16 == 0) && ((uintptr_t)a.y % 16 == 0) && ((size_t)a.T * D * es) % 16 == 0 &&
+           ((size_t)a.T * es) % 16 == 0 && (kAT * D * es) % 16 == 0 && (kAT * es) % 16 == 0 && a.T >= kAT;
+}
+
+template <int D, int AV, typename TIN>
+static cudaError_t launch_stream_async(const StreamArgs& a, unsigned gy, cudaStream_t st) {
+    typedef AsyncTile<D, TIN> L;
+    const int64_t nwarps = (a.B + 31) / 32;
+    const unsigned gx = (unsigned)((nwarps + kAWarps - 1) / kAWarps);
+    const size_t smem = (size_t)kAWarps * 2 * L::STAGE;
+    auto kern = sim_stream_async_kernel<D, AV, TIN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(gx, gy), kAWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int D, typename TIN>
 static cudaError_t launch_stream_d(const StreamArgs& a, cudaStream_t st) {
     const int A = a.v.A;
-    const unsigned gx = (unsigned)((a.B + kStreamBlock - 1) / kStreamBlock);
+    if (async_eligible<D, TIN>(a)) {
+        if (A == 1) return launch_stream_async<D, 1, TIN>(a, 1, st);
+        return launch_stream_async<D, 3, TIN>(a, (unsigned)((A + 2) / 3), st);
+    }
+    const unsigned gx = (unsigned)((a.B + kStreamBlock - 1) / kStreamBlock);      // unaligned shapes: direct loads
     if (A == 1) sim_stream_kernel<D, 1, TIN><<<dim3(gx, 1), kStreamBlock, 0, st>>>(a);
     else sim_stream_kernel<D, 3, TIN><<<dim3(gx, (A + 2) / 3), kStreamBlock, 0, st>>>(a);
     return cudaGetLastError();

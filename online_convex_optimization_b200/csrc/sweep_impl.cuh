@@ -53,40 +53,6 @@ struct SweepArgs {
     SweepPlan plan;
 };
 
-template <int D>
-__device__ __forceinline__ void grad_step(double (&th)[D], const double (&hz)[D], double df) {
-    // theta += g*z, g = 0.5*sign(df) (fast_algorithms.py:27-34,110-111); NaN / zero diff: no step
-    if (df > 0.0 || df < 0.0) {
-        const int sgn = __double2hiint(df) & 0x80000000;
-#pragma unroll
-        for (int j = 0; j < D; ++j)
-            th[j] = th[j] + __hiloint2double(__double2hiint(hz[j]) ^ sgn, __double2loint(hz[j]));
-    }
-}
-
-template <int D>
-__device__ __forceinline__ void ftl_action(const double (&th)[D], double (&x)[D]) {
-    // fast_algorithms.py:37-49, branch-free: 1/sqrt(0) = inf is masked by the select
-    double n2 = th[0] * th[0];
-#pragma unroll
-    for (int j = 1; j < D; ++j) n2 = n2 + th[j] * th[j];
-    const double sc = -(1.0 / sqrt_of_sumsq<D>(n2, th[0]));
-#pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = (n2 == 0.0) ? 0.0 : sc * th[j];
-}
-
-// x *= 1/||x|| iff !(n2 <= 1) (fast_algorithms.py:61-66), branch-free per lane, skipped per warp
-template <int D>
-__device__ __forceinline__ void project_unit_ball(double (&x)[D], double n2, unsigned mask) {
-    const bool need = !(n2 <= 1.0);
-    if (__any_sync(mask, need)) {
-        const double r = need ? sqrt_of_sumsq<D>(n2, x[0]) : 1.0;
-        const double fac = 1.0 / r;                         // 1.0/1.0 == 1.0: untouched lanes stay bit-identical
-#pragma unroll
-        for (int j = 0; j < D; ++j) x[j] = x[j] * fac;
-    }
-}
-
 // resident CTAs per SM the register allocator must allow (more warps hide the serial RNG / fp64 chains)
 #ifndef OCO_SWEEP_MIN_BLOCKS
 #define OCO_SWEEP_MIN_BLOCKS 5

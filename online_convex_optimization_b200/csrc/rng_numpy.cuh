@@ -24,6 +24,12 @@ __device__ const unsigned long long g_zig_wi[256] = OCO_ZIG_WI_BITS_INIT;
 __device__ const unsigned long long g_zig_ki[256] = OCO_ZIG_KI_INIT;
 __device__ const unsigned long long g_zig_fi[256] = OCO_ZIG_FI_BITS_INIT;
 
+// constant-memory copies for the (single-lane, divergent) slow path: no shared-memory pointer has
+// to cross the call boundary and the accesses are uniform per executing lane
+__constant__ unsigned long long c_zig_wi[256] = OCO_ZIG_WI_BITS_INIT;
+__constant__ unsigned long long c_zig_ki[256] = OCO_ZIG_KI_INIT;
+__constant__ unsigned long long c_zig_fi[256] = OCO_ZIG_FI_BITS_INIT;
+
 struct ZigTables {          // shared-memory copy, 6 KB
     double wi[256];
     unsigned long long ki[256];
@@ -211,8 +217,8 @@ __device__ inline double log1p_glibc_fma(double x) {
 // State goes in and out by value so that the fast path keeps it in registers.
 struct ZigSlowRet { double x; uint64_t hi, lo; };
 
-static __device__ __noinline__ ZigSlowRet zig_slow(const ZigTables* tb, uint64_t s_hi, uint64_t s_lo,
-                                            uint64_t inc_hi, uint64_t inc_lo, int idx, uint64_t rabs, double x) {
+static __device__ __noinline__ ZigSlowRet zig_slow(uint64_t s_hi, uint64_t s_lo, uint64_t inc_hi, uint64_t inc_lo,
+                                                   int idx, uint64_t rabs, double x) {
     Pcg64 s; s.hi = s_hi; s.lo = s_lo;
     PcgInc inc; inc.hi = inc_hi; inc.lo = inc_lo;
     ZigSlowRet out;
@@ -228,17 +234,29 @@ static __device__ __noinline__ ZigSlowRet zig_slow(const ZigTables* tb, uint64_t
                 }
             }
         }
-        double f1 = tb->fi[idx], f0 = tb->fi[idx - 1];
-        // exp() here only feeds a comparison; a 1-ulp difference from glibc's exp flips
-        // the outcome with probability ~2^-52 per wedge test (documented in DESIGN.md).
-        if ((f0 - f1) * pcg_double(s, inc) + f1 < exp(-0.5 * x * x)) break;
+        const double f1 = __longlong_as_double((long long)c_zig_fi[idx]);
+        const double f0 = __longlong_as_double((long long)c_zig_fi[idx - 1]);
+        const double yv = (f0 - f1) * pcg_double(s, inc) + f1;
+        const double arg = -0.5 * x * x;
+        // Wedge test yv < exp(arg).  Only the comparison matters, so it is first bracketed with a
+        // float exponential (relative error < 2e-6): outside a +-1e-5 band the outcome is certain and
+        // identical to the double-precision test; inside (probability ~2e-5 per wedge test) the double
+        // exp decides.  (CUDA's exp is <= 1 ulp, glibc's is correctly rounded in all but ~1e-3 of
+        // cases: the two can disagree on the comparison with probability ~2^-52)
+        const double ef = (double)__expf((float)arg);
+        bool accept;
+        if (yv < ef * (1.0 - 1e-5)) accept = true;
+        else if (yv > ef * (1.0 + 1e-5)) accept = false;
+        else accept = yv < exp(arg);
+        if (accept) break;
         // rejected: a fresh attempt, exactly the top of numpy's for(;;)
         uint64_t r = pcg_next64(s, inc);
         idx = (int)(r & 0xff);
         rabs = (r >> 9) & 0x000fffffffffffffULL;
-        x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb->wi[idx];
+        x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) *
+            __longlong_as_double((long long)c_zig_wi[idx]);
         if ((r >> 8) & 1) x = -x;
-        if (rabs < tb->ki[idx]) break;
+        if (rabs < c_zig_ki[idx]) break;
     }
     out.x = x; out.hi = s.hi; out.lo = s.lo;
     return out;
@@ -253,7 +271,7 @@ __device__ __forceinline__ double zig_normal(const ZigTables& tb, Pcg64& s, cons
     double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
     if ((r >> 8) & 1) x = -x;
     if (rabs < tb.ki[idx]) return x;
-    ZigSlowRet o = zig_slow(&tb, s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
+    ZigSlowRet o = zig_slow(s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
     s.hi = o.hi; s.lo = o.lo;
     return o.x;
 }
@@ -267,7 +285,7 @@ __device__ __forceinline__ void zig_skip(const ZigTables& tb, Pcg64& s, const Pc
     if (rabs < tb.ki[idx]) return;
     double x = (__longlong_as_double((long long)(0x4330000000000000ULL | rabs)) - 4503599627370496.0) * tb.wi[idx];
     if ((r >> 8) & 1) x = -x;
-    ZigSlowRet o = zig_slow(&tb, s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
+    ZigSlowRet o = zig_slow(s.hi, s.lo, inc.hi, inc.lo, idx, rabs, x);
     s.hi = o.hi; s.lo = o.lo;
 }
 

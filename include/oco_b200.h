@@ -62,8 +62,8 @@ extern "C" {
 #define OCO_MAX_VARIANTS 64
 #define OCO_MAX_SMART_THRESHOLDS 4
 
-/* comparator_mode for oco_simulate_batch* (d > 8 only; d <= 8 is always exact):
- * 0 = second pass over the sequence, the literal fast_algorithms.py:113-114;
+/* comparator_mode for oco_simulate_batch*:
+ * 0 = second pass over the sequence, the literal fast_algorithms.py:113-114 (bit-exact for d <= 8);
  * 1 = single pass using 0.5|z.a - y| = 0.5(1 - y z.a) when ||z_t|| <= 1, y = +-1 (checked per
  *     row; sequences that violate it fall back to the second pass).  Tolerance 1e-12 relative. */
 #define OCO_COMPARATOR_TWO_PASS 0

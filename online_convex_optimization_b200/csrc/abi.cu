@@ -148,7 +148,7 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int c
         CU(launch_sim_stream_f32(z, y, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, x_last, st));
     else if (d <= kMaxSmallD)
         CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), comparator, regret, cum_loss, comp_loss,
-                             theta_final, x_last, x_trace, st));
+                             theta_final, x_last, x_trace, comparator_mode, st));
     else if (wide_tma_eligible(z, y, in_dtype == OCO_F32, T, d))
         CU(launch_sim_wide_tma(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, comparator_mode, st));
     else    // unaligned shapes: plain coalesced loads

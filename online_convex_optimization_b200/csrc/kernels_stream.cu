@@ -25,6 +25,7 @@ struct StreamArgs {
     const double* tab;
     const double* comparator;    // optional [B][D]: fixed comparator action (exact_ftl.py:255-271) instead of FTL(theta_T)
     double* regret; double* cum; double* comp; double* theta_final; double* x_last; double* x_trace;
+    int comparator_mode;         // 1: single-pass linear comparator when the rows allow it (staged kernel only)
     Variants v;
 };
 
@@ -191,6 +192,7 @@ cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64
                                   cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     StreamArgs a;
+    a.comparator_mode = 0;
     a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.comparator = nullptr;
     a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_last = x_last; a.x_trace = nullptr; a.v = v;
     const dim3 grid((unsigned)((B + kStreamBlock - 1) / kStreamBlock), (unsigned)v.A);
@@ -284,6 +286,13 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
         for (int j = 0; j < D; ++j) th[v][j] = 0.0;
     }
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
+    // OCO_COMPARATOR_LINEAR: vy = sum y_t z_t while playing; if every row has ||z_t|| <= 1 (+1e-6) and
+    // y_t = +-1 then comp = 0.5*(T - a.vy) and the second pass over the sequence is skipped (1e-12 class)
+    const bool want_linear = p.comparator_mode == 1 && !p.comparator;
+    double vy[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) vy[j] = 0.0;
+    bool linear_ok = true;
 
     // one round; PASS 0 = play (fast_algorithms.py:99-111), PASS 1 = comparator (fast_algorithms.py:69-76)
     auto row_step = [&](int pass, int64_t t, const double (&z)[D], double y) {
@@ -291,6 +300,14 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
             double hz[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) hz[j] = 0.5 * z[j];
+            if (want_linear) {
+                double zz = z[0] * z[0];
+#pragma unroll
+                for (int j = 1; j < D; ++j) zz = zz + z[j] * z[j];
+                if (!(zz <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) linear_ok = false;
+#pragma unroll
+                for (int j = 0; j < D; ++j) vy[j] = vy[j] + y * z[j];
+            }
             const double* trow = p.tab + t * A + v0;
 #pragma unroll
             for (int v = 0; v < AV; ++v) {
@@ -329,18 +346,7 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
         }
     };
 
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
-#pragma unroll
-            for (int v = 0; v < AV; ++v) {
-                if (p.comparator && active) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) act[v][j] = p.comparator[b * D + j];
-                } else {
-                    ftl_action<D>(th[v], act[v]);
-                }
-            }
-        }
+    auto run_pass = [&](int pass) {      // inlined at both call sites with a constant `pass`
         if (ntiles > 0) stage_tile(0, 0);
         for (int tile = 0; tile < ntiles; ++tile) {
             const int st = tile & 1;
@@ -352,22 +358,22 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
                 TIN yv[kAT];
                 {
                     uint4 ybuf[(L::YB + 15) / 16];
-#pragma unroll
+    #pragma unroll
                     for (int i = 0; i < L::YB / 16; ++i) ybuf[i] = *reinterpret_cast<const uint4*>(rec + L::ZB + i * 16);
                     const TIN* ye = reinterpret_cast<const TIN*>(ybuf);
-#pragma unroll
+    #pragma unroll
                     for (int r = 0; r < kAT; ++r) yv[r] = ye[r];
                 }
-#pragma unroll
+    #pragma unroll
                 for (int g = 0; g < kAT / L::RG; ++g) {
                     uint4 zbuf[L::GV];
-#pragma unroll
+    #pragma unroll
                     for (int i = 0; i < L::GV; ++i) zbuf[i] = *reinterpret_cast<const uint4*>(rec + (g * L::GV + i) * 16);
                     const TIN* ze = reinterpret_cast<const TIN*>(zbuf);
-#pragma unroll
+    #pragma unroll
                     for (int r = 0; r < L::RG; ++r) {
                         double z[D];
-#pragma unroll
+    #pragma unroll
                         for (int j = 0; j < D; ++j) z[j] = (double)ze[r * D + j];
                         row_step(pass, (int64_t)tile * kAT + g * L::RG + r, z, (double)yv[g * L::RG + r]);
                     }
@@ -380,11 +386,32 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
             const TIN* yb = reinterpret_cast<const TIN*>(yw) + (int64_t)lane * T;
             for (int64_t t = (int64_t)ntiles * kAT; t < T; ++t) {      // ragged tail: direct loads
                 double z[D];
-#pragma unroll
+    #pragma unroll
                 for (int j = 0; j < D; ++j) z[j] = (double)zb[t * D + j];
                 row_step(pass, t, z, (double)yb[t]);
             }
         }
+    };
+
+    run_pass(0);
+    // the staged second pass is a warp-wide affair: skipped only if every sequence of the warp qualifies
+    if (want_linear && !__any_sync(0xffffffffu, active && !linear_ok)) {
+#pragma unroll
+        for (int v = 0; v < AV; ++v) {
+            ftl_action<D>(th[v], act[v]);
+            C[v] = (double)T - dot_seq<D>(act[v], vy);         // comp = 0.5*C
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < AV; ++v) {
+            if (p.comparator && active) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) act[v][j] = p.comparator[b * D + j];
+            } else {
+                ftl_action<D>(th[v], act[v]);
+            }
+        }
+        run_pass(1);
     }
     if (!active) return;
 #pragma unroll
@@ -455,9 +482,10 @@ static cudaError_t launch_stream_t(const StreamArgs& a, int d, cudaStream_t st) 
 cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                               const Variants& v, const double* scale_tab, const double* comparator,
                               double* regret, double* cum, double* comp, double* theta_final, double* x_last,
-                              double* x_trace, cudaStream_t st) {
+                              double* x_trace, int comparator_mode, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     StreamArgs a;
+    a.comparator_mode = comparator_mode;
     a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.comparator = comparator;
     a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_last = x_last; a.x_trace = x_trace; a.v = v;
     return in_f32 ? launch_stream_t<float>(a, d, st) : launch_stream_t<double>(a, d, st);

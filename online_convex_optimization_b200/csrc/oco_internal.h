@@ -64,7 +64,7 @@ cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint6
 cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                               const Variants& v, const double* scale_tab, const double* comparator,
                               double* regret, double* cum, double* comp, double* theta_final, double* x_last,
-                              double* x_trace, cudaStream_t st);
+                              double* x_trace, int comparator_mode, cudaStream_t st);
 // float32 compute mode (algorithms.py semantics), float32 inputs, d <= 8
 cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64_t T, int d,
                                   const Variants& v, const double* scale_tab,

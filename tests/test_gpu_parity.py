@@ -282,3 +282,18 @@ def test_float32_mode_matches_numpy_reference(eng, golden_sim):
     g = alg32.empirical_worst_case_thresholds(np.array([100]), runs=50, base_seed=0)
     g64 = O.empirical_worst_case_thresholds(np.array([100]), runs=50, base_seed=0)
     assert abs(g[100] - g64[100]) <= 1e-5 * g64[100]
+
+
+def test_small_d_linear_comparator(eng):
+    """d <= 8 streamed kernel, single-pass comparator: 1e-12 on clipped rows, exact fallback otherwise."""
+    for d, T, B in ((5, 400, 70), (1, 1000, 33), (8, 100, 40)):
+        zs, ys = zip(*[O.gen_gpath(6, T, r, d) for r in range(B)])
+        z, y = np.stack(zs), np.stack(ys)
+        flags, etas = [0, 1, 0, 0], [R2, R2, 0.2, 5.0]
+        want = O.simulate_batch(z, y, flags, etas)
+        got = eng.simulate_batch(z, y, flags, etas, comparator="linear")
+        assert np.all(np.abs(got - want) <= REL * np.maximum(1.0, np.abs(want))), d
+        z2 = z * 2.5                                   # outside the unit ball: must fall back to the exact pass
+        want2 = O.simulate_batch(z2, y, flags, etas)
+        got2 = eng.simulate_batch(z2, y, flags, etas, comparator="linear")
+        assert (bits(got2) == bits(want2)).all(), d

@@ -114,13 +114,16 @@ OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_d
 
 /* ---- fast_algorithms.simulate_SMART_like (fast_algorithms.py:184-195 -> :118-164), batched;
  * A <= OCO_MAX_SMART_THRESHOLDS (theta_thresh[a], eta0[a]) pairs per sequence, d <= 8.
- * switch_t [B*A] (may be NULL) = step at which the switch test fired, -1 if never. */
+ * switch_t [B*A] (may be NULL) = step at which the switch test fired, -1 if never.
+ * smart_mode 0: the reference's O(T^2) prefix-loss recomputation (:157-158), spread over a warp.
+ * smart_mode 1: O(T) -- in the linear regime (||z_t|| <= 1, y_t = +-1) the leader's prefix loss is
+ *   0.5*((t+1) - s.sum_i y_i z_i); sequences with a violating row are re-run by mode 0. */
 OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                     const double* theta_thresh, const double* eta0, int A,
-                    double* regret, int64_t* switch_t, void* stream);
+                    double* regret, int64_t* switch_t, int smart_mode, void* stream);
 OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                          const double* theta_thresh, const double* eta0, int A,
-                         double* regret, int64_t* switch_t, int device);
+                         double* regret, int64_t* switch_t, int smart_mode, int device);
 
 /* ---- sequence generators (sequence_generation.py:24-100, fast_algorithms.py:231-239).
  * Sequence b is drawn from np.random.Generator(PCG64(SeedSequence([a_b, T, c_b]))) with

@@ -26,8 +26,8 @@ SIGNATURES = {
     "oco_exact_ftl_prefix_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "oco_replay_actions_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i], _i),
     "oco_exact_ftl_prefix_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i], _i),
-    "oco_smart_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp], _i),
-    "oco_smart_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _i], _i),
+    "oco_smart_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _i, _vp], _i),
+    "oco_smart_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _i, _i], _i),
     "oco_gen_sequences": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _i64, _i, _vp, _vp, _vp], _i),
     "oco_gen_sequences_host": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _i64, _i, _vp, _vp, _i], _i),
     "oco_regret_sweep": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),

@@ -292,11 +292,12 @@ OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_d
 // ---------------------------------------------------------------------------------- SMART
 OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                     const double* theta_thresh, const double* eta0, int A,
-                    double* regret, int64_t* switch_t, void* stream) {
+                    double* regret, int64_t* switch_t, int smart_mode, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     if (A > OCO_MAX_SMART_THRESHOLDS) return fail(OCO_ERR_VALUE, "SMART: A <= %d thresholds per call (got %d)", OCO_MAX_SMART_THRESHOLDS, A);
     if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "SMART: d <= %d supported (got %d)", kMaxSmallD, d);
     if (!theta_thresh || !eta0 || (B > 0 && !regret)) return fail(OCO_ERR_VALUE, "theta_thresh / eta0 / regret must not be NULL");
+    if (smart_mode != 0 && smart_mode != 1) return fail(OCO_ERR_VALUE, "unknown smart_mode %d", smart_mode);
     if (B == 0) return OCO_OK;
     cudaStream_t st = (cudaStream_t)stream;
     Etas e; for (int a = 0; a < kMaxVariants; ++a) e.e[a] = a < A ? eta0[a] : 0.0;
@@ -305,13 +306,16 @@ OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t 
     CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
     CU(th.alloc(sizeof(double) * A, st));
     CU(cudaMemcpyAsync(th.p, theta_thresh, sizeof(double) * A, cudaMemcpyHostToDevice, st));
-    CU(launch_smart(z, y, in_dtype == OCO_F32, B, T, d, th.as<double>(), tab.as<double>(), A, regret, switch_t, st));
+    DevBuf fl;
+    if (smart_mode == 1) CU(fl.alloc(sizeof(int) * (size_t)B, st));
+    CU(launch_smart(z, y, in_dtype == OCO_F32, B, T, d, th.as<double>(), tab.as<double>(), A, regret, switch_t, smart_mode,
+                    fl.as<int>(), st));
     return OCO_OK;
 }
 
 OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                          const double* theta_thresh, const double* eta0, int A,
-                         double* regret, int64_t* switch_t, int device) {
+                         double* regret, int64_t* switch_t, int smart_mode, int device) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     if (B == 0) return OCO_OK;
@@ -332,7 +336,7 @@ OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int
         const int64_t nb = std::min<int64_t>(chunk, B - b0);
         CU(cudaMemcpyAsync(zd[i].p, (const char*)z + (size_t)b0 * T * d * es, (size_t)nb * T * d * es, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(yd[i].p, (const char*)y + (size_t)b0 * T * es, (size_t)nb * T * es, cudaMemcpyHostToDevice, s));
-        if (int rc = oco_smart_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, theta_thresh, eta0, A, rd[i].as<double>(), sd[i].as<int64_t>(), s)) return rc;
+        if (int rc = oco_smart_batch(zd[i].p, yd[i].p, in_dtype, nb, T, d, theta_thresh, eta0, A, rd[i].as<double>(), sd[i].as<int64_t>(), smart_mode, s)) return rc;
         CU(cudaMemcpyAsync(regret + b0 * A, rd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
         if (switch_t) CU(cudaMemcpyAsync(switch_t + b0 * A, sd[i].p, (size_t)nb * A * 8, cudaMemcpyDeviceToHost, s));
     }

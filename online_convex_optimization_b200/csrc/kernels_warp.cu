@@ -195,6 +195,8 @@ struct SmartArgs {
     const double* thresh;    // [A]
     int A;
     double* regret; int64_t* switch_t;    // [B][A]
+    const int* only_flagged;              // optional [B]: the exact kernel processes sequence b only if non-zero
+    int* flags;                           // linear kernel: [B] set to 1 when a row violates the precondition
 };
 
 template <int D, typename TIN>
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kSmartWarps * 32) smart_kernel(const SmartArgs
     const int lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * kSmartWarps + (threadIdx.x >> 5);
     if (b >= p.B) return;
+    if (p.only_flagged && p.only_flagged[b] == 0) return;
     const int A = p.A;
     const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * D;
     const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
@@ -298,6 +301,101 @@ __global__ void __launch_bounds__(kSmartWarps * 32) smart_kernel(const SmartArgs
     }
 }
 
+// SMART in the linear regime, O(T*d) instead of O(T^2*d): when every row has ||z_i||_2 <= 1 (+1e-6) and
+// y_i = +-1, the prefix loss of the leader s (fast_algorithms.py:157-158) is 0.5*sum_{i<=t}(1 - y_i z_i.s)
+// = 0.5*((t+1) - s.v_t) with v_t = sum_{i<=t} y_i z_i, so the switch test needs one dot product per round.
+// One thread per sequence, all thresholds at once.  Sequences with a violating row are flagged and
+// re-run by the exact warp kernel.  Tolerance class 1e-12 (the switch test compares against a sum
+// formed in a different order).
+template <int D, typename TIN>
+__global__ void __launch_bounds__(128) smart_linear_kernel(const SmartArgs p) {
+    const int64_t b = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (b >= p.B) return;
+    const int A = p.A;
+    const TIN* __restrict__ zb = (const TIN*)p.z + b * p.T * D;
+    const TIN* __restrict__ yb = (const TIN*)p.y + b * p.T;
+    double thl[D], vy[D], thr[kSmartMaxA][D], total[kSmartMaxA], thresh[kSmartMaxA];
+    int64_t sw[kSmartMaxA];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { thl[j] = 0.0; vy[j] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < kSmartMaxA; ++a) {
+        total[a] = 0.0; sw[a] = -1; thresh[a] = a < A ? p.thresh[a] : 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) thr[a][j] = 0.0;
+    }
+    double ftl_loss = 0.0;
+    int bad = 0, n_unswitched = A;
+    for (int64_t t = 0; t < p.T; ++t) {
+        double z[D], hz[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) { z[j] = (double)zb[t * D + j]; hz[j] = 0.5 * z[j]; }
+        const double y = (double)yb[t];
+        double zz = z[0] * z[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) zz = zz + z[j] * z[j];
+        if (!(zz <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) bad = 1;
+#pragma unroll
+        for (int j = 0; j < D; ++j) vy[j] = vy[j] + y * z[j];
+        double x[D];
+        ftl_action<D>(thl, x);                                   // fast_algorithms.py:140-146
+        const double dff = dot_seq<D>(z, x) - y;
+        grad_step<D>(thl, hz, dff);
+        const double lf = 0.5 * fabs(dff);
+        ftl_loss = ftl_loss + lf;
+#pragma unroll
+        for (int a = 0; a < kSmartMaxA; ++a) {
+            if (a < A) {
+                if (sw[a] >= 0) {                                // :148-154, FTRL on its own theta, global t+1
+                    double xr[D];
+                    action_ftrl<D>(thr[a], __ldg(p.tab + t * A + a), xr);
+                    const double dr = dot_seq<D>(z, xr) - y;
+                    total[a] = total[a] + 0.5 * fabs(dr);
+                    grad_step<D>(thr[a], hz, dr);
+                } else {
+                    total[a] = total[a] + lf;
+                }
+            }
+        }
+        if (n_unswitched > 0) {                                  // :156-160 with the closed-form prefix loss
+            double s[D];
+            ftl_action<D>(thl, s);
+            const double s_loss = 0.5 * ((double)(t + 1) - dot_seq<D>(s, vy));
+#pragma unroll
+            for (int a = 0; a < kSmartMaxA; ++a)
+                if (a < A && sw[a] < 0 && ftl_loss - s_loss >= thresh[a]) { sw[a] = t; --n_unswitched; }
+        }
+    }
+    double s[D];
+    ftl_action<D>(thl, s);                                       // :162-164
+    const double comp = 0.5 * ((double)p.T - dot_seq<D>(s, vy));
+    p.flags[b] = bad;
+#pragma unroll
+    for (int a = 0; a < kSmartMaxA; ++a) {
+        if (a < A) {
+            p.regret[b * A + a] = total[a] - comp;
+            if (p.switch_t) p.switch_t[b * A + a] = sw[a];
+        }
+    }
+}
+
+template <typename TIN>
+static cudaError_t launch_smart_linear_t(const SmartArgs& a, int d, cudaStream_t st) {
+    const unsigned gx = (unsigned)((a.B + 127) / 128);
+    switch (d) {
+    case 1: smart_linear_kernel<1, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 2: smart_linear_kernel<2, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 3: smart_linear_kernel<3, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 4: smart_linear_kernel<4, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 5: smart_linear_kernel<5, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 6: smart_linear_kernel<6, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 7: smart_linear_kernel<7, TIN><<<gx, 128, 0, st>>>(a); break;
+    case 8: smart_linear_kernel<8, TIN><<<gx, 128, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 template <typename TIN>
 static cudaError_t launch_smart_t(const SmartArgs& a, int d, cudaStream_t st) {
     const unsigned gx = (unsigned)((a.B + kSmartWarps - 1) / kSmartWarps);
@@ -315,14 +413,22 @@ static cudaError_t launch_smart_t(const SmartArgs& a, int d, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// mode 0: exact O(T^2) warp kernel; mode 1: linear-regime O(T) kernel, then the exact kernel on the
+// sequences it flagged (flags: device scratch [B] ints, required for mode 1)
 cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                          const double* thresh_dev, const double* scale_tab, int A,
-                         double* regret, int64_t* switch_t, cudaStream_t st) {
+                         double* regret, int64_t* switch_t, int mode, int* flags, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (A < 1 || A > kSmartMaxA) return cudaErrorInvalidValue;
     SmartArgs a;
     a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.thresh = thresh_dev; a.A = A;
-    a.regret = regret; a.switch_t = switch_t;
+    a.regret = regret; a.switch_t = switch_t; a.only_flagged = nullptr; a.flags = flags;
+    if (mode == 1) {
+        if (!flags) return cudaErrorInvalidValue;
+        cudaError_t e = in_f32 ? launch_smart_linear_t<float>(a, d, st) : launch_smart_linear_t<double>(a, d, st);
+        if (e != cudaSuccess) return e;
+        a.only_flagged = flags;
+    }
     return in_f32 ? launch_smart_t<float>(a, d, st) : launch_smart_t<double>(a, d, st);
 }
 

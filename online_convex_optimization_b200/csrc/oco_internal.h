@@ -89,7 +89,7 @@ cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int6
 // SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).
 cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                          const double* thresh_dev, const double* scale_tab, int A,
-                         double* regret, int64_t* switch_t, cudaStream_t st);
+                         double* regret, int64_t* switch_t, int mode, int* flags, cudaStream_t st);
 
 // non-FMA fp64 issue-rate microbenchmark (16 ops per thread per iteration, 256 threads per block)
 cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);

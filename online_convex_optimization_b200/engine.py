@@ -119,8 +119,12 @@ def replay_actions(z, y, actions, *, device: int = 0):
     return {"cum_loss": cum, "comp_loss": comp, "regret": reg}
 
 
-def smart_batch(z, y, theta_threshs, eta0s, *, device: int = 0):
-    """Batched fast_algorithms.simulate_SMART_like -> (regret (B,A), switch_t (B,A))."""
+SMART_MODES = {"exact": 0, "linear": 1}
+
+
+def smart_batch(z, y, theta_threshs, eta0s, *, mode: str = "exact", device: int = 0):
+    """Batched fast_algorithms.simulate_SMART_like -> (regret (B,A), switch_t (B,A)).
+    mode="linear": O(T) prefix loss in the linear regime (see oco_b200.h), exact fallback per sequence."""
     z, y, dt = _prep_zy(z, y)
     B, T, d = z.shape
     th = np.ascontiguousarray(np.atleast_1d(theta_threshs), dtype=np.float64)
@@ -130,7 +134,8 @@ def smart_batch(z, y, theta_threshs, eta0s, *, device: int = 0):
     A = th.size
     reg = np.empty((B, A))
     sw = np.empty((B, A), dtype=np.int64)
-    _lib.check(_lib.load().oco_smart_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(th), _vp(et), A, _vp(reg), _vp(sw), device))
+    _lib.check(_lib.load().oco_smart_batch_host(_vp(z), _vp(y), dt, B, T, d, _vp(th), _vp(et), A, _vp(reg), _vp(sw),
+                                                SMART_MODES[mode], device))
     return reg, sw
 
 
@@ -235,7 +240,7 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
     return {"regret": reg, "cum_loss": cum, "comp_loss": comp, "theta": th}
 
 
-def smart_batch_device(z, y, theta_threshs, eta0s):
+def smart_batch_device(z, y, theta_threshs, eta0s, *, mode: str = "exact"):
     torch = _torch()
     B, T, d = z.shape
     th = np.ascontiguousarray(np.atleast_1d(theta_threshs), dtype=np.float64)
@@ -245,7 +250,8 @@ def smart_batch_device(z, y, theta_threshs, eta0s):
     sw = torch.empty((B, A), dtype=torch.int64, device=z.device)
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().oco_smart_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
-                                               B, T, d, _vp(th), _vp(et), A, _dptr(reg), _dptr(sw), _stream_ptr(torch)))
+                                               B, T, d, _vp(th), _vp(et), A, _dptr(reg), _dptr(sw), SMART_MODES[mode],
+                                               _stream_ptr(torch)))
     return reg, sw
 
 

@@ -68,7 +68,7 @@ def test_argument_validation_is_value_error():
     et = (ctypes.c_double * 1)(1.0)
     rc = lib.oco_regret_sweep(0, 0, 0, None, 4, 10, 6, -1.0, af, et, 1, None, None, None, None, None)
     assert rc == _lib.OCO_ERR_VALUE and b"d <= 5" in lib.oco_last_error()
-    rc = lib.oco_smart_batch(None, None, 1, 0, 4, 3, et, et, 9, None, None, None)
+    rc = lib.oco_smart_batch(None, None, 1, 0, 4, 3, et, et, 9, None, None, 0, None)
     assert rc == _lib.OCO_ERR_VALUE
 
 

@@ -297,3 +297,24 @@ def test_small_d_linear_comparator(eng):
         want2 = O.simulate_batch(z2, y, flags, etas)
         got2 = eng.simulate_batch(z2, y, flags, etas, comparator="linear")
         assert (bits(got2) == bits(want2)).all(), d
+
+
+def test_smart_linear_mode(eng):
+    """O(T) SMART (linear regime): same switch times and regrets (1e-12) as the oracle; exact fallback."""
+    T, B = 600, 40
+    zs, ys = zip(*[O.gen_iid(2025 * (r + 1), T, 0)[:2] for r in range(B // 2)] + [O.gen_gpath(2, T, r, 5) for r in range(B // 2)])
+    z, y = np.stack([np.asarray(a, dtype=np.float64) for a in zs]), np.stack([np.asarray(a, dtype=np.float64) for a in ys])
+    # (a threshold of exactly 0.5 would be a knife edge: with a unit-norm first row the switch test at t = 0 is
+    #  0.5*||z_0|| >= 0.5, decided by the last bit of the row norm -- any reordering may flip it)
+    th, et = [math.sqrt(2 * T), 3.0, 0.75], [R2, R2, R2]
+    want, want_sw = O.smart_batch(z, y, th, et)
+    got, sw = eng.smart_batch(z, y, th, et, mode="linear")
+    assert (sw == want_sw).all()
+    assert np.all(np.abs(got - want) <= REL * np.maximum(1.0, np.abs(want)))
+    z2 = z.copy(); z2[::3] *= 1.7                        # some sequences leave the unit ball -> exact kernel
+    want2, want_sw2 = O.smart_batch(z2, y, th, et)
+    got2, sw2 = eng.smart_batch(z2, y, th, et, mode="linear")
+    assert (sw2 == want_sw2).all()
+    assert np.all(np.abs(got2 - want2) <= REL * np.maximum(1.0, np.abs(want2)))
+    zf, yf, _ = O.gen_flip(1000)
+    assert eng.smart_batch(zf, yf, [math.sqrt(2000)], [R2], mode="linear")[0][0, 0] == O.simulate_smart_like(zf, yf, math.sqrt(2000), R2)

@@ -318,3 +318,23 @@ def test_smart_linear_mode(eng):
     assert np.all(np.abs(got2 - want2) <= REL * np.maximum(1.0, np.abs(want2)))
     zf, yf, _ = O.gen_flip(1000)
     assert eng.smart_batch(zf, yf, [math.sqrt(2000)], [R2], mode="linear")[0][0, 0] == O.simulate_smart_like(zf, yf, math.sqrt(2000), R2)
+
+
+def test_regret_sweep_many_variants_and_tiny_shapes(eng):
+    """More FTRL variants than one thread holds (several groups), duplicate FTL columns, T = 1, B = 1."""
+    flags = [0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0]          # 16 FTRL (2 groups of 8) + 3 FTL columns
+    etas = [0.05 * (i + 1) * R2 for i in range(len(flags))]
+    want = O.regret_sweep(3, 150, 5, 70, 2, flags, etas)
+    got = eng.regret_sweep("gpath", 70, 150, 2, flags, etas, key_a=3, key_c0=5)
+    assert (bits(got["regret"]) == bits(want)).all()
+    assert (got["stats"][:, 0] == want.max(axis=0)).all()
+    for T, B in ((1, 5), (2, 1), (33, 1)):
+        want = O.regret_sweep(0, T, 0, B, 5, [0, 1], [R2, R2])
+        got = eng.regret_sweep("gpath", B, T, 5, [0, 1], [R2, R2])["regret"]
+        assert (bits(got) == bits(want)).all(), (T, B)
+    keys = np.array([[2025, 13 + r] for r in range(9)], dtype=np.uint64)
+    got = eng.regret_sweep("iid", 9, 120, 5, [1] + [0] * 8, [R2 * 2.0 ** (k - 4) for k in range(9)], keys=keys)["regret"]
+    for b in range(9):
+        z, y, _ = O.gen_iid(2025, 120, b)
+        for a in range(9):
+            assert got[b, a] == O.simulate_alg(z, y, 1 if a == 0 else 0, R2 * 2.0 ** (a - 4))

@@ -239,6 +239,9 @@ def test_edge_cases(eng):
     assert got["regret"].shape == (0, 1)
     g, _ = eng.g_sweep([10, 20], runs=0)
     assert (g == 0.0).all()
+    assert (eng.regret_sweep("gpath", 3, 0, 5, [0, 1], [1.0, 1.0])["regret"] == 0.0).all()          # T = 0
+    z0, y0 = eng.gen_sequences("gpath", 2, 0, 5)
+    assert z0.shape == (2, 0, 5) and y0.shape == (2, 0)
     with pytest.raises(ValueError):
         eng.simulate_batch(np.zeros((2, 4, 3)), np.zeros((2, 5)), [0], [1.0])
     with pytest.raises(ValueError):

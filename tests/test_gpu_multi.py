@@ -1,0 +1,54 @@
+"""Multi-GPU test (-m gpu, needs >= 2 visible GPUs; skipped otherwise): a g(T)-style sweep sharded over
+2 ranks with NCCL gives the single-GPU statistics -- MAX bit-identical, SUM within 1e-14."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+R2 = math.sqrt(2.0)
+
+
+def _worker(rank, world, port, n_runs, T, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from online_convex_optimization_b200 import dist as odist
+    reg, stats = odist.regret_sweep_sharded("gpath", n_runs, T, 5, [0, 1], [R2, R2], key_a=0, run_lo=0, want_regret=True)
+    q.put((rank, stats.cpu().numpy(), reg.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from online_convex_optimization_b200 import engine
+    n_runs, T, world = 1001, 300, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_runs, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, st, reg = q.get(timeout=300)
+        got[r] = (st, reg)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = engine.regret_sweep("gpath", n_runs, T, 5, [0, 1], [R2, R2], key_a=0, key_c0=0)
+    full = np.concatenate([got[0][1], got[1][1]], axis=0)
+    assert (full.view(np.uint64) == single["regret"].view(np.uint64)).all()       # same trajectories on any rank
+    for r in range(world):
+        st = got[r][0]
+        assert (st[:, 0] == single["stats"][:, 0]).all()                              # MAX: bit-identical
+        assert (st[:, 3] == n_runs).all()
+        assert np.allclose(st[:, 1], single["stats"][:, 1], rtol=1e-14)
+        assert np.allclose(st[:, 2], single["stats"][:, 2], rtol=1e-14)

@@ -167,8 +167,13 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
     const size_t es = elem_size(in_dtype);
     const size_t seq_bytes = (size_t)T * (d + 1) * es;
     const size_t out_per_seq = (size_t)A * 8 * (3 + (theta_final ? d : 0) + (x_trace ? (size_t)T * d : 0));
-    // chunk so that one buffer set stays <= ~256 MiB; two sets are in flight
-    int64_t chunk = (int64_t)std::max<size_t>(1, (256u << 20) / std::max<size_t>(1, seq_bytes + out_per_seq));
+    // Two buffer sets are in flight (copy of chunk i+1 overlaps the kernel of chunk i).  A trajectory is a
+    // serial chain of T rounds (~2 us each), so a chunk must hold enough sequences for its kernel to be
+    // shorter than its own PCIe copy: up to 2 GiB per set, and at least two chunks when the batch is big.
+    retain_pool_memory();
+    const size_t per_seq = std::max<size_t>(1, seq_bytes + out_per_seq);
+    int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)2 << 30) / per_seq);
+    if ((size_t)B * per_seq > ((size_t)512 << 20)) chunk = std::min<int64_t>(chunk, (B + 1) / 2);
     chunk = std::min<int64_t>(chunk, B);
     DevBuf zd[2], yd[2], rd[2], cd[2], pd[2], td[2], xd[2], ld[2], qd[2];
     for (int i = 0; i < 2; ++i) {
@@ -322,7 +327,9 @@ OCO_API int oco_smart_batch_host(const void* z, const void* y, int in_dtype, int
     StreamPair sp; if (int rc = sp.create()) return rc;
     const size_t es = elem_size(in_dtype);
     const size_t seq_bytes = (size_t)T * (d + 1) * es;
-    int64_t chunk = (int64_t)std::max<size_t>(1, (256u << 20) / std::max<size_t>(1, seq_bytes));
+    retain_pool_memory();
+    int64_t chunk = (int64_t)std::max<size_t>(1, ((size_t)2 << 30) / std::max<size_t>(1, seq_bytes));
+    if ((size_t)B * seq_bytes > ((size_t)512 << 20)) chunk = std::min<int64_t>(chunk, (B + 1) / 2);
     chunk = std::min<int64_t>(chunk, B);
     DevBuf zd[2], yd[2], rd[2], sd[2];
     for (int i = 0; i < 2; ++i) {

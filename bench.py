@@ -82,11 +82,19 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1: do not trust it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sweep_rate(wl, budget_s: float, nthreads: int = 0):
     """Oracle port timed on the host cores: returns (traj_steps_per_s, cores, sample description)."""
     from oracle import oracle as O
     A = len(wl["alg"])
-    cores = nthreads or O.num_threads()
+    cores = nthreads or host_threads()
     n0 = max(cores, 8)
     t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
     dt0 = time.perf_counter() - t0
@@ -102,14 +110,14 @@ def cpu_stream_rate(wl, budget_s: float):
     """Oracle port of the streamed workload (pre-generated sequences, simulation only)."""
     import numpy as np
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = host_threads()
     n = max(cores, 16)
     zs, ys = zip(*[O.gen_gpath(0, wl["T"], r, wl["d"]) for r in range(n)])
     z, y = np.stack(zs), np.stack(ys)
-    O.simulate_batch(z[:cores], y[:cores], wl["alg"], wl["eta"])
+    O.simulate_batch(z[:cores], y[:cores], wl["alg"], wl["eta"], nthreads=cores)
     reps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
-        O.simulate_batch(z, y, wl["alg"], wl["eta"]); reps += 1
+        O.simulate_batch(z, y, wl["alg"], wl["eta"], nthreads=cores); reps += 1
     dt = time.perf_counter() - t0
     return reps * n * len(wl["alg"]) * wl["T"] / dt, cores, f"{n} resident sequences x T={wl['T']} x d={wl['d']}, {reps} passes, simulation only, {dt:.1f} s"
 
@@ -218,7 +226,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     from oracle import oracle as O
-    A = len(wl["alg"]); cores = O.num_threads()
+    A = len(wl["alg"]); cores = host_threads()
     if wl.get("streamed"):      # pre-generated resident sequences, simulation only (what the streamed kernel does)
         v, cores, sample = cpu_stream_rate(wl, max(5.0, min(60.0, 10.0 * args.steps)))
         emit_line({"impl": "reference", "metric": "trajectory-steps/sec", "value": v, "unit": "trajectory-steps/s",
@@ -230,14 +238,14 @@ def run_reference(args, wl):
         return
     per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     n0 = max(cores, 8)
-    t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"])
+    t0 = time.perf_counter(); O.regret_sweep(0, wl["T"], 0, n0, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
     dt0 = time.perf_counter() - t0
     n = max(cores, int(n0 * per_step_budget / max(dt0, 1e-6)))
     for _ in range(args.warmup):
-        O.regret_sweep(0, wl["T"], 0, n, wl["d"], wl["alg"], wl["eta"])
+        O.regret_sweep(0, wl["T"], 0, n, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        O.regret_sweep(0, wl["T"], k * n, n, wl["d"], wl["alg"], wl["eta"])
+        O.regret_sweep(0, wl["T"], k * n, n, wl["d"], wl["alg"], wl["eta"], nthreads=cores)
     dt = time.perf_counter() - t0
     val = args.steps * n * A * wl["T"] / dt
     sample = f"{n} trials/step x T={wl['T']} x A={A}, oracle port (C, OpenMP), generation included"

@@ -341,3 +341,12 @@ def test_regret_sweep_many_variants_and_tiny_shapes(eng):
         z, y, _ = O.gen_iid(2025, 120, b)
         for a in range(9):
             assert got[b, a] == O.simulate_alg(z, y, 1 if a == 0 else 0, R2 * 2.0 ** (a - 4))
+
+
+def test_sweep_large_sample_bit_exact(eng):
+    """10^8 device-generated normals (about 8.5e5 wedge tests, 2.8e4 tail draws through log1p) feeding
+    2e5 fused FTRL trajectories: every regret equals the CPU oracle's bit for bit."""
+    B, T, d = 200_000, 100, 5
+    want = O.regret_sweep(12345, T, 777, B, d, [0], [R2])
+    got = eng.regret_sweep("gpath", B, T, d, [0], [R2], key_a=12345, key_c0=777)["regret"]
+    assert (bits(got) == bits(want)).all()

@@ -80,3 +80,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oco_oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/oco_b200.h compiles as C99 and a C program links against the library."""
+    import shutil
+    import subprocess
+    from online_convex_optimization_b200 import _lib
+    _lib.load()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include <stdio.h>\n#include "oco_b200.h"\n'
+                   'int main(void) { int n = -1; int rc = oco_device_count(&n);\n'
+                   '  int bad = oco_simulate_batch_host(0, 0, 9, OCO_F64, 1, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0);\n'
+                   '  printf("%d %d %d %d %s\\n", oco_abi_version(), rc, n >= 0, bad, oco_last_error()); return 0; }\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-loco_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 4)
+    assert out[0] == "1" and out[1] == "0" and out[2] == "1" and out[3] == "1" and "dtype" in out[4]

@@ -98,9 +98,13 @@ __device__ __forceinline__ void pcg_step(Pcg64& s, const PcgInc& inc) {
     s.lo = lo2; s.hi = hi;
 }
 __device__ __forceinline__ uint64_t pcg_output(const Pcg64& s) {
-    uint64_t x = s.hi ^ s.lo;
-    unsigned rot = (unsigned)(s.hi >> 58);
-    return (x >> rot) | (x << ((64u - rot) & 63u));
+    // XSL-RR: rotr64(hi ^ lo, hi >> 58), as two 32-bit funnel shifts (halves swapped when rot >= 32)
+    const uint64_t x = s.hi ^ s.lo;
+    const unsigned rot = (unsigned)(s.hi >> 58);
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    const uint32_t a = (rot & 32u) ? xh : xl, b = (rot & 32u) ? xl : xh;
+    const uint32_t lo = __funnelshift_r(a, b, rot), hi = __funnelshift_r(b, a, rot);   // shift amount taken mod 32
+    return ((uint64_t)hi << 32) | lo;
 }
 __device__ __forceinline__ uint64_t pcg_next64(Pcg64& s, const PcgInc& inc) {
     pcg_step(s, inc);

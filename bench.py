@@ -206,7 +206,7 @@ def run_streamed(args, wl, *, emit=True, init_dist=True):
                          "traffic": (lambda v: None if v is None else v * passes)(ncu_traffic("sim_wide_tma_kernel<64,16,double>", float(B) * A * T)),
                          "traffic_note": "bytes per launch from the committed ncu capture (linear mode) x passes over the input",
                          "kernel": "sim_wide_tma_kernel<64,16,double>", "algorithmic_bytes_per_trajectory_step": bytes_per_step,
-                         "passes_over_input": passes,
+                         "passes_over_input": passes, "peak_nominal": 8000.0, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "result_check": {"mean_regret": float(reg.mean().item()), "max_regret": float(reg.max().item())},
         }

@@ -107,6 +107,27 @@ OCO_API int oco_exact_ftl_prefix_batch_host(const void* z, const void* y, int in
                                     double* actions, double* cum_loss, double* comp_loss, double* regret,
                                     int* status, int device);
 
+/* ---- general exact-FTL prefix solver: any rows / labels, unit ball norm 0 = l2, 1 = linf, 2 = l1
+ * (exact_ftl.py:67-105 `norm=`), d <= 8.  For l2, sequences in the linear regime take the closed
+ * form above; all others are solved, every prefix independently, by a path-following interior-point
+ * method (Newton on the log-barrier function with the epigraph variables eliminated, see
+ * csrc/kernels_exact.cu) until the duality gap is <= tol * max(1, f(0)), f(0) = 0.5*sum|y_i|
+ * (suggested tol 1e-8, what conic solvers deliver by default), using at most `max_iter` Newton steps
+ * per prefix (suggested 300; 20-30 are typical).  status [B]: 0 = all prefixes converged, n > 0 =
+ * n prefixes stopped at max_iter (treat like the reference's solver failure, exact_ftl.py:125-126).
+ * Prefixes shorter than `first_prefix` are not solved (their actions are zeros; 0 or 1 = solve all,
+ * T = only the full sequence, which is what one ExactFTLNoClip.solve_prefix call needs -- prefixes
+ * are solved independently, so the result is the same bits either way).  actions [B*(T+1)*d] is
+ * required; cum_loss / comp_loss / regret [B] (may be NULL) are the replay of those actions.  An
+ * independent solver, not a restatement of the reference's CVXPY stack: PARITY UNPINNED, validated
+ * against scipy (HiGHS / SLSQP) in the tests. */
+OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d, int norm,
+                                int max_iter, double tol, int64_t first_prefix, double* actions, double* cum_loss, double* comp_loss,
+                                double* regret, int* status, void* stream);
+OCO_API int oco_exact_ftl_general_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d, int norm,
+                                     int max_iter, double tol, int64_t first_prefix, double* actions, double* cum_loss, double* comp_loss,
+                                     double* regret, int* status, int device);
+
 /* ---- exact_ftl.replay_exact_ftl (exact_ftl.py:306-333) for caller-supplied actions [B*(T+1)*d]:
  * cum_loss = sum_t 0.5|z_t.actions[t] - y_t|, comp_loss = 0.5 sum_t |z_t.actions[T] - y_t|. d <= 8. */
 OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,

@@ -24,6 +24,8 @@ SIGNATURES = {
     "oco_simulate_batch": ([_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "oco_simulate_batch_host": ([_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
     "oco_exact_ftl_prefix_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "oco_exact_ftl_general_batch": ([_vp, _vp, _i, _i64, _i64, _i, _i, _i, _dbl, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "oco_exact_ftl_general_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _i, _i, _dbl, _i64, _vp, _vp, _vp, _vp, _vp, _i], _i),
     "oco_replay_actions_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _i], _i),
     "oco_exact_ftl_prefix_batch_host": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i], _i),
     "oco_smart_batch": ([_vp, _vp, _i, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _i, _vp], _i),

@@ -257,6 +257,71 @@ OCO_API int oco_exact_ftl_prefix_batch_host(const void* z, const void* y, int in
     return rc;
 }
 
+OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d, int norm,
+                                int max_iter, double tol, int64_t first_prefix, double* actions, double* cum_loss, double* comp_loss,
+                                double* regret, int* status, void* stream) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
+    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "exact FTL: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (norm < 0 || norm > 2) return fail(OCO_ERR_VALUE, "norm must be 0 (l2), 1 (linf) or 2 (l1)");
+    if (max_iter < 1 || !(tol > 0.0)) return fail(OCO_ERR_VALUE, "need max_iter >= 1 and tol > 0");
+    if (first_prefix < 0 || first_prefix > T + 1) return fail(OCO_ERR_VALUE, "need 0 <= first_prefix <= T + 1");
+    if (B > 0 && (!status || !actions)) return fail(OCO_ERR_VALUE, "status / actions must not be NULL");
+    if (B == 0) return OCO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    retain_pool_memory();
+    DevBuf fl;
+    const int* flagged = nullptr;
+    if (norm == 0) {    // closed form wherever the sequence is in the linear regime; its status = 1 marks the others
+        CU(fl.alloc(sizeof(int) * (size_t)B, st));
+        CU(launch_exact_ftl_linear(z, y, in_dtype == OCO_F32, B, T, d, actions, nullptr, nullptr, nullptr, fl.as<int>(), st));
+        flagged = fl.as<int>();
+    }
+    CU(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, st));
+    CU(launch_exact_ftl_general(z, y, in_dtype == OCO_F32, B, T, d, norm, max_iter, tol, first_prefix, flagged, actions,
+                                status, st));
+    if (cum_loss || comp_loss || regret)
+        CU(launch_replay_actions(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, st));
+    return OCO_OK;
+}
+
+OCO_API int oco_exact_ftl_general_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d, int norm,
+                                     int max_iter, double tol, int64_t first_prefix, double* actions, double* cum_loss, double* comp_loss,
+                                     double* regret, int* status, int device) {
+    if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
+    if (B > 0 && (!status || !actions)) return fail(OCO_ERR_VALUE, "status / actions must not be NULL");
+    DeviceGuard g; if (int rc = g.set(device)) return rc;
+    if (B == 0) return OCO_OK;
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t es = elem_size(in_dtype);
+    int rc = OCO_OK;
+    {
+        DevBuf zd, yd, ad, cd, pd, rd, sd;
+        const size_t na = (size_t)B * (T + 1) * d * 8;
+        bool ok = zd.alloc((size_t)B * T * d * es, st) == cudaSuccess && yd.alloc((size_t)B * T * es, st) == cudaSuccess &&
+                  ad.alloc(na, st) == cudaSuccess && cd.alloc((size_t)B * 8, st) == cudaSuccess &&
+                  pd.alloc((size_t)B * 8, st) == cudaSuccess && rd.alloc((size_t)B * 8, st) == cudaSuccess &&
+                  sd.alloc((size_t)B * 4, st) == cudaSuccess;
+        if (!ok) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
+        if (!rc && T > 0 && (cudaMemcpyAsync(zd.p, z, (size_t)B * T * d * es, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                             cudaMemcpyAsync(yd.p, y, (size_t)B * T * es, cudaMemcpyHostToDevice, st) != cudaSuccess))
+            rc = fail(OCO_ERR_RUNTIME, "host-to-device copy failed");
+        if (!rc) rc = oco_exact_ftl_general_batch(zd.p, yd.p, in_dtype, B, T, d, norm, max_iter, tol, first_prefix, ad.as<double>(),
+                                                  cd.as<double>(), pd.as<double>(), rd.as<double>(), sd.as<int>(), st);
+        if (!rc) {
+            bool c = cudaMemcpyAsync(status, sd.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                     cudaMemcpyAsync(actions, ad.p, na, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (cum_loss) c = c && cudaMemcpyAsync(cum_loss, cd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (comp_loss) c = c && cudaMemcpyAsync(comp_loss, pd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (regret) c = c && cudaMemcpyAsync(regret, rd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            if (!c) rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
+        }
+    }
+    cudaError_t es_ = cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (!rc && es_ != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "exact FTL (general) failed: %s", cudaGetErrorString(es_));
+    return rc;
+}
+
 OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum_loss, double* comp_loss, double* regret, int device) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;

@@ -84,6 +84,10 @@ cudaError_t launch_sim_wide_tma(const void* z, const void* y, int in_f32, int64_
                                 const Variants& v, const double* scale_tab,
                                 double* regret, double* cum, double* comp, double* theta_final, int comparator_mode,
                                 cudaStream_t st);
+// general exact-FTL prefix solver (ADMM), any unit ball (0 = l2, 1 = linf, 2 = l1), d <= 8
+cudaError_t launch_exact_ftl_general(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d, int norm,
+                                     int max_iter, double tol, int64_t first_prefix, const int* only_flagged,
+                                     double* actions, int* status, cudaStream_t st);
 cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
 // SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).

@@ -107,6 +107,24 @@ def exact_ftl_prefix_batch(z, y, *, want_actions: bool = True, device: int = 0):
     return {"actions": act, "cum_loss": cum, "comp_loss": comp, "regret": reg, "status": status}
 
 
+NORMS = {"l2": 0, "linf": 1, "l1": 2}
+
+
+def exact_ftl_general_batch(z, y, *, norm: str = "l2", max_iter: int = 300, tol: float = 1e-8, first_prefix: int = 0,
+                            device: int = 0):
+    """General exact-FTL prefix actions + replay (any rows / labels, unit l2 / linf / l1 ball; see oco_b200.h).
+    first_prefix = T solves only the full sequence (shorter prefixes' actions are zeros unless the closed form gave them).
+    Returns dict(actions (B,T+1,d), cum_loss, comp_loss, regret (B,), status (B,) = prefixes that used up max_iter Newton steps)."""
+    z, y, dt = _prep_zy(z, y)
+    B, T, d = z.shape
+    act = np.empty((B, T + 1, d))
+    cum, comp, reg = np.empty(B), np.empty(B), np.empty(B)
+    status = np.zeros(B, dtype=np.int32)
+    _lib.check(_lib.load().oco_exact_ftl_general_batch_host(_vp(z), _vp(y), dt, B, T, d, NORMS[norm], int(max_iter), float(tol), int(first_prefix),
+                                                            _vp(act), _vp(cum), _vp(comp), _vp(reg), _vp(status), device))
+    return {"actions": act, "cum_loss": cum, "comp_loss": comp, "regret": reg, "status": status}
+
+
 def replay_actions(z, y, actions, *, device: int = 0):
     """Batched exact_ftl.replay_exact_ftl: z (B,T,d), y (B,T), actions (B,T+1,d) -> dict of (B,) arrays."""
     z, y, dt = _prep_zy(z, y)

@@ -1,14 +1,21 @@
 """Twin of the reference's ``exact_ftl`` module (exact_ftl.py:62-453): same class / function
 names, arguments, return types and exceptions, with the solves done by the batched CUDA path.
 
-Scope of this round (DESIGN.md "Exact FTL"): the unit **l2** ball in the *linear regime*
-(every row ||z_t||_2 <= 1 and y_t in {-1,+1}), which is what every generator in
-sequence_generation.py produces and therefore everything exact_ftl_driver.py runs.  There the
-reference's SOCP (exact_ftl.py:83-105) has the closed-form optimum v/||v||, v = sum y_i z_i
-(0 on ties), computed for all prefixes by ``oco_exact_ftl_prefix_batch``.  Inputs outside the
-regime, and the l1 / linf balls, need a general conic solver: they raise ``RuntimeError``
-(the exception exact_ftl.py:125-126 raises when the solver fails) instead of returning a
-wrong optimum.  PARITY UNPINNED: the reference's arithmetic is CVXPY's (not installed, unpinned).
+Two device solvers sit behind ``ExactFTLNoClip`` (DESIGN.md "Exact FTL"):
+
+* unit **l2** ball in the *linear regime* (every row ||z_t||_2 <= 1 and y_t in {-1,+1} -- what
+  every generator in sequence_generation.py produces, hence everything exact_ftl_driver.py
+  runs): the reference's SOCP (exact_ftl.py:83-105) has the closed-form optimum v/||v||,
+  v = sum y_i z_i (0 on ties), computed for all prefixes by ``oco_exact_ftl_prefix_batch``;
+* everything else (rows outside the ball, real-valued labels, the linf / l1 balls of
+  exact_ftl.py:91-96) with d <= 8: the interior-point solver of ``oco_exact_ftl_general_batch``,
+  duality gap <= ``solver_opts["tol"]`` * max(1, f(0)) (default 1e-8) within
+  ``solver_opts["max_iter"]`` (default 300) Newton steps per prefix; a prefix that does not converge raises the
+  ``RuntimeError`` exact_ftl.py:125-126 raises when its conic solver fails.
+
+PARITY UNPINNED: the reference's arithmetic is CVXPY's (not installed, unpinned); where the
+optimum is not unique (k < d rows, ties) the two solvers may return different minimisers of
+the same objective.
 """
 from __future__ import annotations
 
@@ -27,11 +34,21 @@ def _ensure_float64_contiguous(arr: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(arr, dtype=np.float64)
 
 
-def _solve_prefixes(z: np.ndarray, y: np.ndarray, *, want_actions: bool = True) -> dict:
-    res = engine.exact_ftl_prefix_batch(z[None], y[None], want_actions=want_actions)
-    if int(res["status"][0]) != 0:
+def _solve_prefixes(z: np.ndarray, y: np.ndarray, *, norm: str = "l2", solver_opts: Optional[dict] = None,
+                    only_last: bool = False) -> dict:
+    """All prefix optima of one sequence (only the full-length one when ``only_last``)."""
+    opts = solver_opts or {}
+    if norm == "l2" or z.shape[1] == 1:            # for d = 1 the three unit balls coincide
+        res = engine.exact_ftl_prefix_batch(z[None], y[None], want_actions=True)
+        if int(res["status"][0]) == 0:
+            return res
+    if z.shape[1] > 8:
         raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime "
-                           "(a row has ||z||_2 > 1 or a label is not +-1; the general conic solve is not implemented)")
+                           "(a row has ||z||_2 > 1 or a label is not +-1, and the general solver covers d <= 8)")
+    res = engine.exact_ftl_general_batch(z[None], y[None], norm=norm, max_iter=int(opts.get("max_iter", 300)),
+                                         tol=float(opts.get("tol", 1e-8)), first_prefix=z.shape[0] if only_last else 0)
+    if int(res["status"][0]) != 0:
+        raise RuntimeError(f"Exact FTL (no clip) failed: status=max_iter_reached ({int(res['status'][0])} prefixes)")
     return res
 
 
@@ -47,9 +64,9 @@ class ExactFTLNoClip:
         self.solver_opts = {} if solver_opts is None else dict(solver_opts)
         if self.norm not in ("l2", "linf", "l1"):
             raise ValueError("norm must be one of {'l2','linf','l1'}")
-        if self.norm != "l2" and self.d > 1:
+        if self.norm != "l2" and self.d > 8:
             raise RuntimeError(f"Exact FTL (no clip) failed: status=unsupported_norm_{self.norm} "
-                               "(only the l2 ball is implemented; for d = 1 all three balls coincide)")
+                               "(the linf / l1 solver covers d <= 8)")
         self._Z_buf = np.zeros((self.T_max, self.d), dtype=np.float64)
         self._y_buf = np.zeros(self.T_max, dtype=np.float64)
         self._w_buf = np.zeros(self.T_max, dtype=np.float64)
@@ -59,7 +76,7 @@ class ExactFTLNoClip:
         t = self._last_length
         if t == 0:
             return np.zeros(self.d, dtype=np.float64)
-        res = _solve_prefixes(self._Z_buf[:t], self._y_buf[:t])
+        res = _solve_prefixes(self._Z_buf[:t], self._y_buf[:t], norm=self.norm, solver_opts=self.solver_opts, only_last=True)
         return np.asarray(res["actions"][0, t], dtype=np.float64)
 
     def reset_buffers(self) -> None:
@@ -139,7 +156,8 @@ def compute_prefix_actions(solver: ExactFTLNoClip, z: np.ndarray, y: np.ndarray)
     solver._set_prefix(z_arr, y_arr, T)
     if T == 0:
         return np.zeros((1, d), dtype=np.float64)
-    return np.asarray(_solve_prefixes(z_arr, y_arr)["actions"][0], dtype=np.float64)
+    res = _solve_prefixes(z_arr, y_arr, norm=solver.norm, solver_opts=solver.solver_opts)
+    return np.asarray(res["actions"][0], dtype=np.float64)
 
 
 def replay_exact_ftl(z: np.ndarray, y: np.ndarray, actions: np.ndarray) -> RunResult:

@@ -119,10 +119,20 @@ def test_exact_ftl_twin_api_and_known_answers():
         ex.replay_exact_ftl(z, y, acts[:-1])
     with pytest.raises(ValueError):
         ex.ExactFTLNoClip(d=3, T_max=4, norm="l3")
+    # outside the linear regime and on the linf / l1 balls the general solver takes over (same API)
+    big = ex.compute_prefix_actions(ex.ExactFTLNoClip(d=3, T_max=40), z * 5.0, y)
+    assert big.shape == (41, 3) and (np.linalg.norm(big, axis=1) <= 1.0 + 1e-9).all()
+    s1 = ex.ExactFTLNoClip(d=3, T_max=40, norm="l1")
+    a1 = ex.compute_prefix_actions(s1, z, y)
+    assert (np.abs(a1).sum(axis=1) <= 1.0 + 1e-9).all()
+    last = s1.solve_prefix(z[:17], y[:17])                            # one prefix == the batched row (same objective value)
+    f = lambda x: 0.5 * np.abs(z[:17] @ x - y[:17]).sum()
+    assert abs(f(last) - f(a1[17])) <= 1e-6 * max(1.0, f(last))
+    assert ex.run_ftl_exact(z, y, norm="linf").regret >= -1e-6
+    with pytest.raises(RuntimeError):                                 # a solve that cannot converge reports failure
+        ex.compute_prefix_actions(ex.ExactFTLNoClip(d=3, T_max=40, solver_opts={"max_iter": 2}), z * 5.0, y)
     with pytest.raises(RuntimeError):
-        ex.compute_prefix_actions(ex.ExactFTLNoClip(d=3, T_max=40), z * 5.0, y)   # outside the linear regime
-    with pytest.raises(RuntimeError):
-        ex.ExactFTLNoClip(d=3, T_max=4, norm="l1")
+        ex.ExactFTLNoClip(d=9, T_max=4, norm="l1")
     # run_ftrl with the exact comparator == oracle FTRL play + comparator loss at the exact action
     r = ex.run_ftrl(z, y, eta0=R2, comparator_action=acts[-1])
     o = O.simulate_alg(z, y, 0, R2, trace=True)
@@ -162,3 +172,73 @@ def test_driver_twin_float32_columns(golden_stats):
     for k in ("FTRL", "FTL"):
         want = np.array([hexf(v) for v in rec["stats"][k][0]])
         assert np.all(np.abs(got[k][0] - want) <= 1e-5 * np.maximum(1.0, np.abs(want)))
+
+
+# ------------------------------------------------------------------ general exact FTL (ADMM) vs scipy
+def _obj(x, z, y):
+    return 0.5 * np.abs(z @ x - y).sum()
+
+
+def _scipy_opt(z, y, norm):
+    """Optimal value of min_{||x||_p<=1} 0.5*sum|z x - y| from an independent solver (HiGHS LP / SLSQP)."""
+    from scipy.optimize import linprog, minimize
+    k, d = z.shape
+    if norm == "linf":
+        c = np.concatenate([np.zeros(d), 0.5 * np.ones(k)])
+        A = np.block([[z, -np.eye(k)], [-z, -np.eye(k)]])
+        r = linprog(c, A_ub=A, b_ub=np.concatenate([y, -y]), bounds=[(-1, 1)] * d + [(0, None)] * k, method="highs")
+        return r.fun
+    if norm == "l1":
+        c = np.concatenate([np.zeros(2 * d), 0.5 * np.ones(k)])
+        A = np.block([[z, -z, -np.eye(k)], [-z, z, -np.eye(k)], [np.ones((1, 2 * d)), np.zeros((1, k))]])
+        r = linprog(c, A_ub=A, b_ub=np.concatenate([y, -y, [1.0]]), bounds=[(0, None)] * (2 * d + k), method="highs")
+        return r.fun
+    cons = [{"type": "ineq", "fun": lambda v: v[d:] - (z @ v[:d] - y)}, {"type": "ineq", "fun": lambda v: v[d:] + (z @ v[:d] - y)},
+            {"type": "ineq", "fun": lambda v: 1.0 - v[:d] @ v[:d]}]
+    best = np.inf
+    for x0 in (np.zeros(d), np.full(d, 0.2), -np.full(d, 0.2)):
+        v0 = np.concatenate([x0, np.abs(z @ x0 - y) + 0.1])
+        r = minimize(lambda v: 0.5 * v[d:].sum(), v0, constraints=cons, method="SLSQP", options={"maxiter": 1000, "ftol": 1e-13})
+        x = r.x[:d] / max(1.0, np.linalg.norm(r.x[:d]))
+        best = min(best, _obj(x, z, y))
+    return best
+
+
+@pytest.mark.parametrize("norm", ["l2", "linf", "l1"])
+def test_exact_ftl_general_solver_vs_scipy(norm):
+    """Outside the linear regime (rows up to norm ~2.5, real-valued labels) the batched interior-point solver reaches
+    the optimum of an independent solver: never meaningfully worse (HiGHS is exact for linf / l1; SLSQP is a weaker
+    reference for l2, hence the looser bound there), and strictly feasible."""
+    from online_convex_optimization_b200 import engine
+    rng = np.random.default_rng(7)
+    B, T, d = 4, 40, 3
+    z = rng.standard_normal((B, T, d)) * 0.9
+    y = rng.standard_normal((B, T))
+    res = engine.exact_ftl_general_batch(z, y, norm=norm)
+    assert (res["status"] == 0).all(), res["status"]
+    assert (res["actions"][:, 0] == 0).all()
+    pnorm = {"l2": 2, "linf": np.inf, "l1": 1}[norm]
+    for b in range(B):
+        for k in (1, 2, 5, 17, 40):
+            x = res["actions"][b, k]
+            assert np.linalg.norm(x, pnorm) < 1.0
+            f, f_ref = _obj(x, z[b, :k], y[b, :k]), _scipy_opt(z[b, :k], y[b, :k], norm)
+            f0 = 0.5 * np.abs(y[b, :k]).sum()
+            assert f <= f_ref + (2e-6 if norm == "l2" else 2e-8) * max(1.0, f0), (norm, b, k, f, f_ref)
+        rep = O.replay_actions(z[b], y[b], res["actions"][b])
+        assert abs(res["regret"][b] - rep["regret"]) <= 1e-10 * max(1.0, abs(rep["regret"]))
+    # prefixes are solved independently: asking for the last one only gives the same bits
+    last = engine.exact_ftl_general_batch(z, y, norm=norm, first_prefix=T)
+    assert (last["actions"][:, T].view(np.uint64) == res["actions"][:, T].view(np.uint64)).all()
+    assert (last["actions"][:, :T] == 0).all() and (last["status"] == 0).all()
+    tight = engine.exact_ftl_general_batch(z, y, norm=norm, tol=1e-10)      # tolerance is honoured
+    for b in range(B):
+        d8, d10 = _obj(res["actions"][b, T], z[b], y[b]), _obj(tight["actions"][b, T], z[b], y[b])
+        assert -1e-10 * T <= d8 - d10 <= 1e-8 * max(1.0, 0.5 * np.abs(y[b]).sum())
+    starved = engine.exact_ftl_general_batch(z, y, norm=norm, max_iter=2)
+    assert (starved["status"] > 0).all()
+    if norm == "l2":     # sequences inside the linear regime keep the closed form, bit for bit
+        zs, ys = O.gen_gpath(4, 60, 1, d)
+        mixed = engine.exact_ftl_general_batch(np.stack([zs, zs * 3.0]), np.stack([ys, ys]))
+        assert (mixed["status"] == 0).all()
+        assert (mixed["actions"][0].view(np.uint64) == O.exact_ftl_l2_prefix(zs, ys).view(np.uint64)).all()

@@ -181,7 +181,9 @@ OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int
 
 /* ---- known-answer probes of the device generator (tests): what = 0 raw uint64, 1 standard
  * normals, 2 random() doubles, 3 choice([-1,1]) labels, 4 SeedSequence state words, 5 log1p(-U);
- * n_skip normals are consumed first.  out: HOST buffer of n 8-byte items. */
+ * n_skip normals are consumed first.  out: HOST buffer of n 8-byte items.
+ * what = 6 checks the kernels' branch-free reciprocal against IEEE division: n threads x n_skip
+ * pseudo-random doubles each (seed a); out[0] (uint64) = number of differing results (must be 0). */
 OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device);
 
 /* ---- scratch (the sweep kernel's row slab, scale tables) is allocated stream-ordered and kept cached

@@ -553,7 +553,7 @@ OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int
 }
 
 OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device) {
-    if (!out || n < 0 || n_skip < 0 || what < 0 || what > 5) return fail(OCO_ERR_VALUE, "bad rng probe arguments");
+    if (!out || n < 0 || n_skip < 0 || what < 0 || what > 6) return fail(OCO_ERR_VALUE, "bad rng probe arguments");
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     if (n == 0) return OCO_OK;
     void* d = nullptr;

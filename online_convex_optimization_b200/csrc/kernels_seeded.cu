@@ -190,7 +190,35 @@ __global__ void rng_probe_kernel(int what, uint64_t a, uint64_t b, uint64_t c, i
     else if (what == 3) { LabelCursor lc; lc.s = s; lc.cur = 0; for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = lc.next(i, inc); }
     else if (what == 5) for (int64_t i = 0; i < n; ++i) ((double*)out)[i] = log1p_glibc_fma(-pcg_double(s, inc));
 }
+// what == 6: rcp_inrange(r) vs the compiler's 1.0 / r over n_skip values per thread of n threads' worth
+// of pseudo-random doubles (both signs, exponents spread over [2^-1000, 2^1000] and, every other
+// draw, over the [1, 2^12) range the kernels actually divide by); out[0] = number of mismatching bit patterns.
+__global__ void rcp_check_kernel(uint64_t seed, int64_t per_thread, unsigned long long* mismatches) {
+    uint64_t x = seed + 0x9e3779b97f4a7c15ull * (uint64_t)(blockIdx.x * (int64_t)blockDim.x + threadIdx.x + 1);
+    unsigned long long bad = 0;
+    for (int64_t i = 0; i < per_thread; ++i) {
+        x += 0x9e3779b97f4a7c15ull;                       // splitmix64
+        uint64_t v = x;
+        v = (v ^ (v >> 30)) * 0xbf58476d1ce4e5b9ull;
+        v = (v ^ (v >> 27)) * 0x94d049bb133111ebull;
+        v ^= v >> 31;
+        const uint64_t mant = v & 0xfffffffffffffull, sign = v >> 63;
+        const uint64_t e11 = (v >> 52) & 0x7ff;
+        const uint64_t ex = (i & 1) ? 1023 + (e11 % 12) : 23 + (e11 % 2001);   // biased exponent
+        const double r = __longlong_as_double((long long)((sign << 63) | (ex << 52) | mant));
+        const double a = rcp_inrange(r), b = 1.0 / r;
+        bad += __double_as_longlong(a) != __double_as_longlong(b);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 cudaError_t launch_rng_probe(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, cudaStream_t st) {
+    if (what == 6) {
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)n * 8, st);
+        if (e != cudaSuccess) return e;
+        rcp_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n_skip, (unsigned long long*)out);
+        return cudaGetLastError();
+    }
     rng_probe_kernel<<<1, 32, 0, st>>>(what, a, b, c, n_skip, n, out);
     return cudaGetLastError();
 }

@@ -59,8 +59,15 @@ struct GPathStream {                      // fast_algorithms.py:231-239
     __device__ __forceinline__ void row(const ZigTables& tb, double (&z)[D], int& ybit) {
 #pragma unroll
         for (int j = 0; j < D; ++j) z[j] = zig_normal(tb, s, inc);
-        double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
-        double inv = 1.0 / (nrm > 1.0 ? nrm : 1.0);      // z *= 1.0 / np.maximum(norms, 1.0)
+        double nrm;
+        if constexpr (D == 1) {
+            // sqrt(fl(z*z)) == |z| for 1 < |z| < 1e145, and both sides are <= 1 together otherwise, which is
+            // all the clip below looks at: no square root (and nothing for the compiler to speculate)
+            nrm = fabs(z[0]);
+        } else {
+            nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+        }
+        double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0); // z *= 1.0 / np.maximum(norms, 1.0); 1 <= norm < 1e3
 #pragma unroll
         for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
         ybit = 0;

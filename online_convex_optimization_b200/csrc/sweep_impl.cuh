@@ -87,13 +87,17 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
             st.init(tb, ka, T, kc, p.p_flip, p.family);
             uint32_t word = 0;
-            for (int t = 0; t < T; ++t) {
-                E ze[D]; int ybit;
-                st.row(tb, ze, ybit);
+            {
+                E* __restrict__ zw = zs;                                  // running pointers: no index arithmetic per step
+                for (int t = 0; t < T; ++t) {
+                    E ze[D]; int ybit;
+                    st.row(tb, ze, ybit);
 #pragma unroll
-                for (int j = 0; j < D; ++j) zs[(int64_t)(t * D + j) * kSweepBlock] = ze[j];
-                word |= (uint32_t)ybit << (t & 31);
-                if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = word; word = 0; }
+                    for (int j = 0; j < D; ++j) zw[j * kSweepBlock] = ze[j];
+                    zw += D * kSweepBlock;
+                    word |= (uint32_t)ybit << (t & 31);
+                    if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = word; word = 0; }
+                }
             }
             st.begin_labels();
 
@@ -114,13 +118,15 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
 #pragma unroll
             for (int j = 0; j < D; ++j) zn[j] = T > 0 ? zs[(int64_t)j * kSweepBlock] : (E)0;
             uint32_t prov = 0;
-            for (int t = 0; t < T; ++t) {
+            const E* __restrict__ zr = zs;                                // row t; the prefetch reads row t + 1
+            const double* __restrict__ tp = trow;                         // scales of step t
+            for (int t = 0; t < T; ++t, zr += D * kSweepBlock, tp += NF) {
                 double z[D], hz[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) { z[j] = (double)zn[j]; hz[j] = 0.5 * z[j]; }
                 if (t + 1 < T) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) zn[j] = zs[(int64_t)((t + 1) * D + j) * kSweepBlock];
+                    for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
                 }
                 if ((t & 31) == 0) { prov = ys[(int64_t)(t >> 5) * kSweepBlock]; word = 0; }
                 const double y = (double)st.label(t, (int)((prov >> (t & 31)) & 1u));
@@ -129,7 +135,16 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
 
                 if (NFTL > 0 && do_ftl) {
                     double x[D];
-                    ftl_action<D>(thl, x);
+                    if constexpr (D == 1) {
+                        // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal
+                        const double n2 = thl[0] * thl[0];
+                        const bool ok = n2 >= 1e-290 && n2 <= 1e290;
+                        double rc = rcp_inrange(ok ? fabs(thl[0]) : 1.0);
+                        if (!ok) rc = 1.0 / sqrt(n2);                          // theta == 0 (masked below) or out of range
+                        x[0] = (n2 == 0.0) ? 0.0 : -rc * thl[0];
+                    } else {
+                        ftl_action<D>(thl, x);
+                    }
                     const double df = dot_seq<D>(z, x) - y;
                     Sl = Sl + fabs(df);
                     grad_step<D>(thl, hz, df);
@@ -139,25 +154,61 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 if constexpr (NF % 2 == 0) {
 #pragma unroll
                     for (int k = 0; k < NF; k += 2) {
-                        const double2 v = __ldg(reinterpret_cast<const double2*>(trow + (int64_t)t * NF + k));
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(tp + k));
                         sc[k] = v.x; sc[k + 1] = v.y;
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) sc[k] = __ldg(trow + (int64_t)t * NF + k);
+                    for (int k = 0; k < NF; ++k) sc[k] = __ldg(tp + k);
                 }
+                if constexpr (D == 1 && NF > 1) {
+                    // The NF variants are independent chains: form all actions first, project them
+                    // together (one vote, branch-free reciprocals that the scheduler can interleave),
+                    // then take all the steps.  fast_algorithms.py:52-66, 105-111
+                    double x1[NF], n2v[NF];
+                    int top = 0;                                             // max over k of the high word of n2 (n2 >= 0 or NaN)
 #pragma unroll
-                for (int k = 0; k < NF; ++k) {                   // fast_algorithms.py:52-66, 105-111
-                    double x[D];
+                    for (int k = 0; k < NF; ++k) {
+                        x1[k] = sc[k] * thr[k][0];
+                        n2v[k] = x1[k] * x1[k];
+                        top = max(top, __double2hiint(n2v[k]));
+                    }
+                    // some n2 >= 1.0 in the warp (n2 == 1.0 exactly is sorted out per lane below)
+                    if (__any_sync(mask, top >= 0x3ff00000)) {
+                        if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
 #pragma unroll
-                    for (int j = 0; j < D; ++j) x[j] = sc[k] * thr[k][j];
-                    double n2 = x[0] * x[0];
+                            for (int k = 0; k < NF; ++k) {
+                                double xx[1] = {x1[k]};
+                                project_unit_ball<1>(xx, n2v[k], mask);
+                                x1[k] = xx[0];
+                            }
+                        } else {
+                            // sqrt(fl(x*x)) == |x|, and x * (1/|x|) == x * |1/x|; idle lanes multiply by 1/1 = 1
 #pragma unroll
-                    for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
-                    project_unit_ball<D>(x, n2, mask);
-                    const double df = dot_seq<D>(z, x) - y;
-                    Sr[k] = Sr[k] + fabs(df);
-                    grad_step<D>(thr[k], hz, df);
+                            for (int k = 0; k < NF; ++k)
+                                x1[k] = x1[k] * fabs(rcp_inrange(!(n2v[k] <= 1.0) ? x1[k] : 1.0));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {
+                        const double df = z[0] * x1[k] - y;
+                        Sr[k] = Sr[k] + fabs(df);
+                        grad_step<D>(thr[k], hz, df);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {                   // fast_algorithms.py:52-66, 105-111
+                        double x[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) x[j] = sc[k] * thr[k][j];
+                        double n2 = x[0] * x[0];
+#pragma unroll
+                        for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                        project_unit_ball<D>(x, n2, mask);
+                        const double df = dot_seq<D>(z, x) - y;
+                        Sr[k] = Sr[k] + fabs(df);
+                        grad_step<D>(thr[k], hz, df);
+                    }
                 }
             }
 
@@ -169,13 +220,14 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             // rows are fetched kPF steps at a time: the compare step is only ~5 fp64 ops per variant, so many
             // loads must be in flight per warp to cover the HBM latency
             constexpr int kPF = (D == 1) ? 8 : (D == 2 ? 4 : 2);
-            for (int t0 = 0; t0 < T; t0 += kPF) {
+            const E* __restrict__ zc = zs;
+            for (int t0 = 0; t0 < T; t0 += kPF, zc += kPF * D * kSweepBlock) {
                 E zb[kPF][D];
 #pragma unroll
                 for (int i = 0; i < kPF; ++i) {
 #pragma unroll
                     for (int j = 0; j < D; ++j)
-                        zb[i][j] = (t0 + i < T) ? zs[(int64_t)((t0 + i) * D + j) * kSweepBlock] : (E)0;
+                        zb[i][j] = (t0 + i < T) ? zc[(i * D + j) * kSweepBlock] : (E)0;
                 }
                 if ((t0 & 31) == 0) word = ys[(int64_t)(t0 >> 5) * kSweepBlock];
 #pragma unroll

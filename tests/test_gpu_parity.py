@@ -48,6 +48,14 @@ def test_device_rng_tail_and_log1p(eng, golden_rng):
     assert (bits(eng.rng_probe(5, (3, 4, 5), 20000)) == bits(O.log1p(-u))).all()
 
 
+def test_rcp_inrange_matches_division(eng):
+    """The branch-free reciprocal the d = 1 paths use (row clip, FTL action, FTRL projection) returns the bits of
+    IEEE 1.0 / r: 2^29 pseudo-random operands, half over [2^-1000, 2^1000], half over [1, 2^12), both signs."""
+    for seed in (1, 2):
+        out = eng.rng_probe(6, (seed, 0, 0), 1 << 16, n_skip=1 << 12)
+        assert int(out.view(np.uint64)[0]) == 0
+
+
 @pytest.mark.parametrize("d", [1, 2, 5, 8, 64])
 def test_gen_gpath_bit_exact(eng, d):
     T = 257 if d < 64 else 96

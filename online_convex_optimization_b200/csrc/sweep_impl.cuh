@@ -71,16 +71,18 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int64_t chunk = item / groups;
         const int g = (int)(item - chunk * groups);
-        const int64_t b = chunk * kSweepBlock + tid;
-        const bool active = b < p.B;
-        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        // lanes past the end of the batch replay the last sequence (results discarded), so that every warp
+        // stays converged and the votes below take the full mask
+        const bool active = chunk * kSweepBlock + tid < p.B;
+        const int64_t b = active ? chunk * kSweepBlock + tid : p.B - 1;
+        constexpr unsigned mask = 0xffffffffu;
         const int nf = min(NF, p.plan.n_ftrl - g * NF);          // live FTRL variants of this group (may be <= 0)
         const bool do_ftl = NFTL > 0 && g == 0 && p.plan.n_ftl > 0;
         double reg_r[NF], reg_l = 0.0;
 #pragma unroll
         for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
 
-        if (active) {
+        {
             // ---- phase 0: generate the rows once (fast_algorithms.py:231-236 / sequence_generation.py:61-66)
             Stream st;
             const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
@@ -137,11 +139,11 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                     double x[D];
                     if constexpr (D == 1) {
                         // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal
+                        // (theta == 0 plays -0.0 instead of 0.0: z*x is a zero either way and df = -y exactly)
                         const double n2 = thl[0] * thl[0];
-                        const bool ok = n2 >= 1e-290 && n2 <= 1e290;
-                        double rc = rcp_inrange(ok ? fabs(thl[0]) : 1.0);
-                        if (!ok) rc = 1.0 / sqrt(n2);                          // theta == 0 (masked below) or out of range
-                        x[0] = (n2 == 0.0) ? 0.0 : -rc * thl[0];
+                        double rc = rcp_inrange(thl[0]);                       // garbage unless 1e-290 <= n2 <= 1e290
+                        if (!(n2 >= 1e-290 && n2 <= 1e290)) rc = (n2 == 0.0) ? 1.0 : 1.0 / sqrt(n2);
+                        x[0] = -fabs(rc) * thl[0];
                     } else {
                         ftl_action<D>(thl, x);
                     }
@@ -183,10 +185,12 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                                 x1[k] = xx[0];
                             }
                         } else {
-                            // sqrt(fl(x*x)) == |x|, and x * (1/|x|) == x * |1/x|; idle lanes multiply by 1/1 = 1
+                            // sqrt(fl(x*x)) == |x|, and x * (1/|x|) == x * |1/x|; lanes with n2 <= 1 keep x
 #pragma unroll
-                            for (int k = 0; k < NF; ++k)
-                                x1[k] = x1[k] * fabs(rcp_inrange(!(n2v[k] <= 1.0) ? x1[k] : 1.0));
+                            for (int k = 0; k < NF; ++k) {
+                                const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
+                                if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
+                            }
                         }
                     }
 #pragma unroll
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             if (NFTL > 0 && do_ftl) {
                 const double cum = 0.5 * Sl, comp = 0.5 * Cl;
                 reg_l = cum - comp;
-                for (int c = 0; c < p.plan.n_ftl; ++c) {
+                for (int c = 0; active && c < p.plan.n_ftl; ++c) {
                     const int64_t o = b * A + p.plan.ftl_col[c];
                     if (p.regret) p.regret[o] = reg_l;
                     if (p.cum) p.cum[o] = cum;
@@ -262,9 +266,9 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                     const double cum = 0.5 * Sr[k], comp = 0.5 * Cr[k];
                     reg_r[k] = cum - comp;
                     const int64_t o = b * A + p.plan.ftrl_col[g * NF + k];
-                    if (p.regret) p.regret[o] = reg_r[k];
-                    if (p.cum) p.cum[o] = cum;
-                    if (p.comp) p.comp[o] = comp;
+                    if (active && p.regret) p.regret[o] = reg_r[k];
+                    if (active && p.cum) p.cum[o] = cum;
+                    if (active && p.comp) p.comp[o] = comp;
                 }
             }
         }

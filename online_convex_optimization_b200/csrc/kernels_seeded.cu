@@ -51,6 +51,7 @@ void make_sweep_plan(const Variants& v, const Etas& e, SweepPlan* pl) {
         else pl->ftl_col[pl->n_ftl++] = a;
     }
     pl->nf_tpl = pl->n_ftrl <= 1 ? 1 : (pl->n_ftrl <= 4 ? 4 : 8);
+    if (const char* e = getenv("OCO_SWEEP_NF")) { const int v = atoi(e); if (v == 1 || v == 4 || v == 8) pl->nf_tpl = v; }   // tuning knob
     pl->groups = pl->n_ftrl == 0 ? 1 : (pl->n_ftrl + pl->nf_tpl - 1) / pl->nf_tpl;
 }
 

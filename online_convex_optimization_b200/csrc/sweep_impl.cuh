@@ -115,6 +115,13 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             for (int j = 0; j < D; ++j) thl[j] = 0.0;
             const double* __restrict__ trow = p.tab + (int64_t)g * T * NF;
 
+            // d = 1: the comparator -(1/sqrt(th*th))*th is -th*fl(1/|th|), i.e. one of +-1, +-w (w = 1 - 2^-53) or 0,
+            // so the comparator losses of ALL variants are among four running sums that depend on the sequence
+            // only; they are accumulated here in the reference's order (fast_algorithms.py:69-76) and phase 2
+            // -- a second pass over the rows, three fp64 ops per variant and step -- is not needed.
+            double cand[4] = {0.0, 0.0, 0.0, 0.0};                         // sum |c*z - y| for c = +1, -1, +w, -w
+            const double kW = __longlong_as_double(0x3fefffffffffffffLL);
+
             // ---- phase 1: play (fast_algorithms.py:99-111); rows prefetched one step ahead
             E zn[D];
 #pragma unroll
@@ -122,6 +129,24 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             uint32_t prov = 0;
             const E* __restrict__ zr = zs;                                // row t; the prefetch reads row t + 1
             const double* __restrict__ tp = trow;                         // scales of step t
+            // the FTRL scales of step t + 1 are fetched at the END of step t, when the step's temporaries are dead:
+            // their (L1-hit) latency hides behind the label / row work at the top of the next step
+            double scn[NF];
+            auto load_scales = [&](const double* __restrict__ q) {
+                if constexpr (NF % 2 == 0) {
+#pragma unroll
+                    for (int k = 0; k < NF; k += 2) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(q + k));
+                        scn[k] = v.x; scn[k + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) scn[k] = __ldg(q + k);
+                }
+            };
+#pragma unroll
+            for (int k = 0; k < NF; ++k) scn[k] = 0.0;
+            if (T > 0) load_scales(tp);
             for (int t = 0; t < T; ++t, zr += D * kSweepBlock, tp += NF) {
                 double z[D], hz[D];
 #pragma unroll
@@ -134,6 +159,14 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 const double y = (double)st.label(t, (int)((prov >> (t & 31)) & 1u));
                 word |= (y > 0.0 ? 1u : 0u) << (t & 31);
                 if ((t & 31) == 31 || t == T - 1) ys[(int64_t)(t >> 5) * kSweepBlock] = word;
+
+                if constexpr (D == 1) {
+                    const double pw = z[0] * kW;                            // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
+                    cand[0] = cand[0] + fabs(z[0] - y);
+                    cand[1] = cand[1] + fabs(z[0] + y);
+                    cand[2] = cand[2] + fabs(pw - y);
+                    cand[3] = cand[3] + fabs(pw + y);
+                }
 
                 if (NFTL > 0 && do_ftl) {
                     double x[D];
@@ -153,16 +186,8 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 }
 
                 double sc[NF];
-                if constexpr (NF % 2 == 0) {
 #pragma unroll
-                    for (int k = 0; k < NF; k += 2) {
-                        const double2 v = __ldg(reinterpret_cast<const double2*>(tp + k));
-                        sc[k] = v.x; sc[k + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) sc[k] = __ldg(tp + k);
-                }
+                for (int k = 0; k < NF; ++k) sc[k] = scn[k];
                 if constexpr (D == 1 && NF > 1) {
                     // The NF variants are independent chains: form all actions first, project them
                     // together (one vote, branch-free reciprocals that the scheduler can interleave),
@@ -214,6 +239,7 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                         grad_step<D>(thr[k], hz, df);
                     }
                 }
+                if (t + 1 < T) load_scales(tp + NF);
             }
 
             // ---- phase 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114, 69-76)
@@ -221,11 +247,29 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
 #pragma unroll
             for (int k = 0; k < NF; ++k) { ftl_action<D>(thr[k], ar[k]); Cr[k] = 0.0; }
             ftl_action<D>(thl, al);
+            bool second_pass = true;
+            if constexpr (D == 1) {
+                second_pass = false;
+                // a == 0 (theta == 0): every term is |+-0 - y| = 1, the sum is T exactly
+                auto pick = [&](double a, double& C) {
+                    if (a == 1.0) C = cand[0]; else if (a == -1.0) C = cand[1];
+                    else if (a == kW) C = cand[2]; else if (a == -kW) C = cand[3];
+                    else if (a == 0.0) C = (double)T; else second_pass = true;   // not reachable for finite theta; exact fallback
+                };
+#pragma unroll
+                for (int k = 0; k < NF; ++k) pick(ar[k][0], Cr[k]);
+                if (NFTL > 0 && do_ftl) pick(al[0], Cl);
+                if (second_pass) {
+                    Cl = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) Cr[k] = 0.0;
+                }
+            }
             // rows are fetched kPF steps at a time: the compare step is only ~5 fp64 ops per variant, so many
             // loads must be in flight per warp to cover the HBM latency
             constexpr int kPF = (D == 1) ? 8 : (D == 2 ? 4 : 2);
             const E* __restrict__ zc = zs;
-            for (int t0 = 0; t0 < T; t0 += kPF, zc += kPF * D * kSweepBlock) {
+            for (int t0 = 0; second_pass && t0 < T; t0 += kPF, zc += kPF * D * kSweepBlock) {
                 E zb[kPF][D];
 #pragma unroll
                 for (int i = 0; i < kPF; ++i) {

@@ -272,6 +272,17 @@ def ncu_traffic(kernel: str, units_per_launch: float):
         return None
 
 
+def ncu_utilisation(kernel: str):
+    """Issue-slot and fp64-pipe utilisation of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json
+    <- profiles/r01_ncu_summary.md): north_star's stated bound for sequences generated on the device."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[kernel]
+        return {"issue_active_pct": rec["issue_active_pct"], "fp64_pipe_active_pct": rec["fp64_pipe_active_pct"],
+                "source": "profiles/r01_ncu_summary.md (ncu --set full, not measured in this run)"}
+    except Exception:
+        return None
+
+
 def _quiet_stdout():
     """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.
     Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
@@ -400,7 +411,8 @@ def main():
                          "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak,
                          "traffic": ncu_traffic(kname, float(B) * A * T), "kernel": kname,
                          "algorithmic_ops_per_trajectory_step": alg_ops,
-                         "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)"},
+                         "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)",
+                         "ncu": ncu_utilisation(kname)},
             "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
                              "mean_regret_per_variant": [float(v) for v in st[:, 1] / np.maximum(st[:, 3], 1)]},
         }

@@ -161,6 +161,23 @@ def test_exact_driver_twin_small():
     assert np.allclose(st["FTL (exact)"][0], fast["FTL"][0], rtol=1e-9, atol=1e-9)
 
 
+def test_c2_exact_vs_fast_ftl_1e4_trials_bit_exact():
+    """BASELINE configs[1]: exact FTL vs fast (linearised) FTL on the same 1e4 sequences.  In the linear regime both
+    play -theta/||theta|| = v/||v||; the closed-form kernel uses the fast path's operation order, so the iterates
+    (and the regrets) agree bit for bit, not just to solver tolerance."""
+    from online_convex_optimization_b200 import engine
+    from online_convex_optimization_b200._lib import FAM_IID, FAM_NOISY
+    B, T, d = 10000, 100, 5
+    keys = np.array([[2025 * (b // 16 + 1), 13 + b % 16] for b in range(B)], dtype=np.uint64)
+    for fam in (FAM_IID, FAM_NOISY):
+        z, y = engine.gen_sequences(fam, B, T, d, keys=keys, p_flip=0.1)
+        ex = engine.exact_ftl_prefix_batch(z, y)
+        sim = engine.simulate_batch(z, y, [1], [1.0], full=True, trace=True)
+        assert (ex["status"] == 0).all()
+        assert (ex["actions"][:, :T].view(np.uint64) == sim["x_trace"][:, 0].view(np.uint64)).all()
+        assert (ex["regret"] == sim["regret"][:, 0]).all() and (ex["cum_loss"] == sim["cum_loss"][:, 0]).all()
+
+
 def test_driver_twin_float32_columns(golden_stats):
     """driver.py twin (float32-state algorithms): within 1e-5 of the float64 golden statistics."""
     from online_convex_optimization_b200 import driver as dr

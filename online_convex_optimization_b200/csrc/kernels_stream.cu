@@ -288,7 +288,13 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
     // OCO_COMPARATOR_LINEAR: vy = sum y_t z_t while playing; if every row has ||z_t|| <= 1 (+1e-6) and
     // y_t = +-1 then comp = 0.5*(T - a.vy) and the second pass over the sequence is skipped (1e-12 class)
-    const bool want_linear = p.comparator_mode == 1 && !p.comparator;
+    // D == 1: the comparator is one of +-1, +-(1 - 2^-53), 0, so its loss is one of four running sums kept during
+    // the play pass (exact, see sweep_impl.cuh / DESIGN.md sec. 3): one pass over the input instead of two
+    constexpr bool kCand = (D == 1);
+    const bool use_cand = kCand && !p.comparator;
+    double cand[5] = {0.0, 0.0, 0.0, 0.0, 0.0};               // sum |c*z - y| for c = +1, -1, +w, -w, 0
+    const double kW = __longlong_as_double(0x3fefffffffffffffLL);
+    const bool want_linear = p.comparator_mode == 1 && !p.comparator && !use_cand;
     double vy[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) vy[j] = 0.0;
@@ -307,6 +313,16 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
                 if (!(zz <= 1.0 + 1e-6) || !(y == 1.0 || y == -1.0)) linear_ok = false;
 #pragma unroll
                 for (int j = 0; j < D; ++j) vy[j] = vy[j] + y * z[j];
+            }
+            if constexpr (kCand) {
+                if (use_cand) {
+                    const double pw = z[0] * kW;
+                    cand[0] = cand[0] + fabs(z[0] - y);
+                    cand[1] = cand[1] + fabs(z[0] + y);
+                    cand[2] = cand[2] + fabs(pw - y);
+                    cand[3] = cand[3] + fabs(pw + y);
+                    cand[4] = cand[4] + fabs(y);                 // c = 0: |+-0 - y|
+                }
             }
             const double* trow = p.tab + t * A + v0;
 #pragma unroll
@@ -394,8 +410,29 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
     };
 
     run_pass(0);
+    bool cand_done = false;
+    if constexpr (kCand) {
+        if (use_cand) {
+            bool miss = false;
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                ftl_action<D>(th[v], act[v]);
+                const double a = act[v][0];
+                if (a == 1.0) C[v] = cand[0]; else if (a == -1.0) C[v] = cand[1];
+                else if (a == kW) C[v] = cand[2]; else if (a == -kW) C[v] = cand[3];
+                else if (a == 0.0) C[v] = cand[4];
+                else miss = true;                                // NaN / out-of-range theta: literal second pass
+            }
+            cand_done = !__any_sync(0xffffffffu, active && miss);
+            if (!cand_done) {
+#pragma unroll
+                for (int v = 0; v < AV; ++v) C[v] = 0.0;
+            }
+        }
+    }
     // the staged second pass is a warp-wide affair: skipped only if every sequence of the warp qualifies
-    if (want_linear && !__any_sync(0xffffffffu, active && !linear_ok)) {
+    if (cand_done) {
+    } else if (want_linear && !__any_sync(0xffffffffu, active && !linear_ok)) {
 #pragma unroll
         for (int v = 0; v < AV; ++v) {
             ftl_action<D>(th[v], act[v]);

@@ -8,7 +8,9 @@
 //            stream (numpy draws them after all normals) and packed 32 per word into the slab;
 //            one optional FTL trajectory and NF FTRL trajectories live in registers.
 //   Phase 2  compare: the comparator of fast_algorithms.py:113-114 needs the FINAL theta, so the
-//            rows and label words stream back once more.
+//            rows and label words stream back once more (D > 1).  For D == 1 the comparator can
+//            only be +-1, +-(1 - 2^-53) or 0, so phase 1 keeps the four candidate loss sums and
+//            phase 2 is a table lookup.
 //   Inputs never exist in the reference's [B][T][d] layout and never cross PCIe; the slab is
 //   private to a thread (it re-reads only what it wrote), sized by the number of resident
 //   threads, not by B.  Per trajectory-step the kernel moves (8 + 16)*D/A bytes of HBM/L2 traffic

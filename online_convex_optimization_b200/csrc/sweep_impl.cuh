@@ -38,6 +38,7 @@
 namespace oco {
 
 constexpr int kSweepBlock = 128;
+constexpr int kRowAhead = 3;      // phase 1 prefetch distance (rows) into L1
 
 struct SweepArgs {
     uint64_t key_a;          // first entropy word (base_seed / run_seed) when keys == nullptr
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             double cand[4] = {0.0, 0.0, 0.0, 0.0};                         // sum |c*z - y| for c = +1, -1, +w, -w
             const double kW = __longlong_as_double(0x3fefffffffffffffLL);
 
-            // ---- phase 1: play (fast_algorithms.py:99-111); rows prefetched one step ahead
+            // ---- phase 1: play (fast_algorithms.py:99-111); rows prefetched into L1 kRowAhead steps ahead
             E zn[D];
 #pragma unroll
             for (int j = 0; j < D; ++j) zn[j] = T > 0 ? zs[(int64_t)j * kSweepBlock] : (E)0;
@@ -153,9 +154,13 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 double z[D], hz[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) { z[j] = (double)zn[j]; hz[j] = 0.5 * z[j]; }
-                if (t + 1 < T) {
+                // Row t + 1 is loaded at the END of this step (below), not here: held across the whole step the
+                // compiler spills it and the spill store waits out the full HBM latency (27 % of all stall
+                // samples before this change).  Row t + kRowAhead is pulled towards L2 / L1 now instead.
+                if (t + kRowAhead < T) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                    for (int j = 0; j < D; ++j)
+                        asm volatile("prefetch.global.L1 [%0];" :: "l"(zr + (kRowAhead * D + j) * kSweepBlock));
                 }
                 if ((t & 31) == 0) { prov = ys[(int64_t)(t >> 5) * kSweepBlock]; word = 0; }
                 const double y = (double)st.label(t, (int)((prov >> (t & 31)) & 1u));
@@ -241,7 +246,11 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                         grad_step<D>(thr[k], hz, df);
                     }
                 }
-                if (t + 1 < T) load_scales(tp + NF);
+                if (t + 1 < T) {
+                    load_scales(tp + NF);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                }
             }
 
             // ---- phase 2: comparator = FTL action of the final theta (fast_algorithms.py:113-114, 69-76)

@@ -79,6 +79,10 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
     SweepArgs a;
     a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = (int)T; a.B = B; a.family = family; a.p_flip = p_flip;
     a.tab = sweep_tab; a.regret = regret; a.cum = cum; a.comp = comp; a.partials = partials; a.plan = plan;
+    {   // test hook: take the literal second pass even where the d = 1 candidate sums apply (tests/test_gpu_parity.py)
+        const char* e = getenv("OCO_SWEEP_FORCE_SECOND_PASS");
+        a.force_second_pass = (e && e[0] == '1') ? 1 : 0;
+    }
     if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);
     if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_iid(a, d, st);
     return cudaErrorInvalidValue;

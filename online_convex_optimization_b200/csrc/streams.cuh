@@ -48,6 +48,7 @@ __device__ __forceinline__ F np_pairwise_sumsq(const F (&z)[D]) {
 template <int D>
 struct GPathStream {                      // fast_algorithms.py:231-239
     typedef double elem_t;
+    static constexpr bool kProvLabels = false;   // labels do not depend on the rows (row() leaves ybit = 0)
     PcgInc inc;
     Pcg64 s;
     LabelCursor lab;
@@ -79,6 +80,7 @@ struct GPathStream {                      // fast_algorithms.py:231-239
 template <int D>
 struct IidStream {                        // sequence_generation.py:54-90
     typedef float elem_t;
+    static constexpr bool kProvLabels = true;    // label = sign(z.u) from row(), then possibly flipped by label()
     PcgInc inc;
     Pcg64 s;
     float u[D];

@@ -38,7 +38,10 @@
 namespace oco {
 
 constexpr int kSweepBlock = 128;
-constexpr int kRowAhead = 3;      // phase 1 prefetch distance (rows) into L1
+#ifndef OCO_SWEEP_ROW_AHEAD
+#define OCO_SWEEP_ROW_AHEAD 3
+#endif
+constexpr int kRowAhead = OCO_SWEEP_ROW_AHEAD;      // phase 1 prefetch distance (rows) into L1
 
 struct SweepArgs {
     uint64_t key_a;          // first entropy word (base_seed / run_seed) when keys == nullptr
@@ -46,6 +49,7 @@ struct SweepArgs {
     const uint64_t* keys;    // optional device [B][2] explicit (a, c) pairs
     int64_t B; int T;
     int family;
+    int force_second_pass;   // test hook (see launch_sweep)
     double p_flip;
     const double* tab;       // [groups][T][NF] FTRL scales -(eta0/sqrt(t+1)), padded with -0.0
     void* slab_z;            // [gridDim.x][T][D][128] elem_t rows
@@ -100,8 +104,10 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
 #pragma unroll
                     for (int j = 0; j < D; ++j) zw[j * kSweepBlock] = ze[j];
                     zw += D * kSweepBlock;
-                    word |= (uint32_t)ybit << (t & 31);
-                    if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = word; word = 0; }
+                    if constexpr (Stream::kProvLabels) {
+                        word |= (uint32_t)ybit << (t & 31);
+                        if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = word; word = 0; }
+                    }
                 }
             }
             st.begin_labels();
@@ -122,6 +128,8 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             // so the comparator losses of ALL variants are among four running sums that depend on the sequence
             // only; they are accumulated here in the reference's order (fast_algorithms.py:69-76) and phase 2
             // -- a second pass over the rows, three fp64 ops per variant and step -- is not needed.
+            // (and the final labels need not be kept for it: the never-taken fallback regenerates them)
+            constexpr bool kKeepLabels = !(D == 1 && !Stream::kProvLabels);
             double cand[4] = {0.0, 0.0, 0.0, 0.0};                         // sum |c*z - y| for c = +1, -1, +w, -w
             const double kW = __longlong_as_double(0x3fefffffffffffffLL);
 
@@ -162,10 +170,15 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                     for (int j = 0; j < D; ++j)
                         asm volatile("prefetch.global.L1 [%0];" :: "l"(zr + (kRowAhead * D + j) * kSweepBlock));
                 }
-                if ((t & 31) == 0) { prov = ys[(int64_t)(t >> 5) * kSweepBlock]; word = 0; }
+                if constexpr (Stream::kProvLabels) {
+                    if ((t & 31) == 0) prov = ys[(int64_t)(t >> 5) * kSweepBlock];
+                }
                 const double y = (double)st.label(t, (int)((prov >> (t & 31)) & 1u));
-                word |= (y > 0.0 ? 1u : 0u) << (t & 31);
-                if ((t & 31) == 31 || t == T - 1) ys[(int64_t)(t >> 5) * kSweepBlock] = word;
+                if constexpr (kKeepLabels) {                              // final labels for the phase-2 pass
+                    if ((t & 31) == 0) word = 0;
+                    word |= (y > 0.0 ? 1u : 0u) << (t & 31);
+                    if ((t & 31) == 31 || t == T - 1) ys[(int64_t)(t >> 5) * kSweepBlock] = word;
+                }
 
                 if constexpr (D == 1) {
                     const double pw = z[0] * kW;                            // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
@@ -270,10 +283,22 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
 #pragma unroll
                 for (int k = 0; k < NF; ++k) pick(ar[k][0], Cr[k]);
                 if (NFTL > 0 && do_ftl) pick(al[0], Cl);
+                if (p.force_second_pass) second_pass = true;
                 if (second_pass) {
                     Cl = 0.0;
 #pragma unroll
                     for (int k = 0; k < NF; ++k) Cr[k] = 0.0;
+                    if constexpr (!kKeepLabels) {                           // rebuild the label words from the stream
+                        Stream s2;
+                        s2.init(tb, ka, T, kc, p.p_flip, p.family);
+                        for (int t = 0; t < T; ++t) { E tmp[D]; int yb; s2.row(tb, tmp, yb); }
+                        s2.begin_labels();
+                        uint32_t w2 = 0;
+                        for (int t = 0; t < T; ++t) {
+                            w2 |= ((double)s2.label(t, 0) > 0.0 ? 1u : 0u) << (t & 31);
+                            if ((t & 31) == 31 || t == T - 1) { ys[(int64_t)(t >> 5) * kSweepBlock] = w2; w2 = 0; }
+                        }
+                    }
                 }
             }
             // rows are fetched kPF steps at a time: the compare step is only ~5 fp64 ops per variant, so many

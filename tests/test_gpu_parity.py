@@ -351,6 +351,20 @@ def test_regret_sweep_many_variants_and_tiny_shapes(eng):
             assert got[b, a] == O.simulate_alg(z, y, 1 if a == 0 else 0, R2 * 2.0 ** (a - 4))
 
 
+def test_sweep_d1_candidate_sums_equal_literal_second_pass(eng, monkeypatch):
+    """d = 1: the comparator losses picked from the four candidate running sums are the bits of the literal second
+    pass (which finite theta never needs; OCO_SWEEP_FORCE_SECOND_PASS=1 forces it, labels regenerated from the stream)."""
+    alg, eta = [1] + [0] * 8, [R2] + [R2 * s for s in (0.125, 0.25, 0.5, 1, 2, 4, 8, 16)]
+    for fam, T in (("gpath", 700), ("gpath", 33), ("iid", 257)):
+        kw = dict(key_a=3, key_c0=5) if fam == "gpath" else dict(key_a=2025, key_c0=13)
+        a = eng.regret_sweep(fam, 300, T, 1, alg, eta, full=True, **kw)
+        monkeypatch.setenv("OCO_SWEEP_FORCE_SECOND_PASS", "1")
+        b = eng.regret_sweep(fam, 300, T, 1, alg, eta, full=True, **kw)
+        monkeypatch.delenv("OCO_SWEEP_FORCE_SECOND_PASS")
+        for k in ("regret", "cum_loss", "comp_loss"):
+            assert (a[k].view(np.uint64) == b[k].view(np.uint64)).all(), (fam, T, k)
+
+
 def test_sweep_large_sample_bit_exact(eng):
     """10^8 device-generated normals (about 8.5e5 wedge tests, 2.8e4 tail draws through log1p) feeding
     2e5 fused FTRL trajectories: every regret equals the CPU oracle's bit for bit."""

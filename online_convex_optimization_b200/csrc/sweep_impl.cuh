@@ -165,10 +165,18 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 // Row t + 1 is loaded at the END of this step (below), not here: held across the whole step the
                 // compiler spills it and the spill store waits out the full HBM latency (27 % of all stall
                 // samples before this change).  Row t + kRowAhead is pulled towards L2 / L1 now instead.
-                if (t + kRowAhead < T) {
+                // (D > 1 has the registers to hold the next row across the step: it is loaded here, a full step ahead.)
+                if constexpr (D == 1) {
+                    if (t + kRowAhead < T) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j)
-                        asm volatile("prefetch.global.L1 [%0];" :: "l"(zr + (kRowAhead * D + j) * kSweepBlock));
+                        for (int j = 0; j < D; ++j)
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(zr + (kRowAhead * D + j) * kSweepBlock));
+                    }
+                } else {
+                    if (t + 1 < T) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                    }
                 }
                 if constexpr (Stream::kProvLabels) {
                     if ((t & 31) == 0) prov = ys[(int64_t)(t >> 5) * kSweepBlock];
@@ -261,8 +269,10 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
                 }
                 if (t + 1 < T) {
                     load_scales(tp + NF);
+                    if constexpr (D == 1) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                        for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                    }
                 }
             }
 
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 
             }
             // rows are fetched kPF steps at a time: the compare step is only ~5 fp64 ops per variant, so many
             // loads must be in flight per warp to cover the HBM latency
-            constexpr int kPF = (D == 1) ? 8 : (D == 2 ? 4 : 2);
+            constexpr int kPF = (D == 1) ? 8 : 4;
             const E* __restrict__ zc = zs;
             for (int t0 = 0; second_pass && t0 < T; t0 += kPF, zc += kPF * D * kSweepBlock) {
                 E zb[kPF][D];

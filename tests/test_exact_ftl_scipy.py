@@ -5,33 +5,15 @@ checked against an independent general-purpose solver (scipy SLSQP on the epigra
 reference's own solver stack (CVXPY + conic solver) is not installed here (parity unpinned)."""
 import numpy as np
 import pytest
-from scipy.optimize import minimize
 
+from oracle import exact_ftl_scipy as XS
 from oracle import oracle as O
 
-
-def _objective(x, z, y):
-    return 0.5 * np.abs(z @ x - y).sum()
+_objective = XS.objective
 
 
 def _scipy_solve(z, y):
-    k, d = z.shape
-    # variables (x, s): min 0.5*sum(s)  s.t.  s >= +-(z x - y),  ||x||^2 <= 1
-    cons = [{"type": "ineq", "fun": lambda v: v[d:] - (z @ v[:d] - y)},
-            {"type": "ineq", "fun": lambda v: v[d:] + (z @ v[:d] - y)},
-            {"type": "ineq", "fun": lambda v: 1.0 - v[:d] @ v[:d]}]
-    best = None
-    for x0 in (np.zeros(d), np.full(d, 0.1), -np.full(d, 0.1)):
-        v0 = np.concatenate([x0, np.abs(z @ x0 - y) + 0.1])
-        r = minimize(lambda v: 0.5 * v[d:].sum(), v0, constraints=cons, method="SLSQP", options={"maxiter": 500, "ftol": 1e-12})
-        x = r.x[:d]
-        n = np.linalg.norm(x)
-        if n > 1.0:
-            x = x / n
-        f = _objective(x, z, y)
-        if best is None or f < best[0]:
-            best = (f, x)
-    return best
+    return XS.solve(z, y, "l2")
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
@@ -56,3 +38,21 @@ def test_tie_break_is_the_centre():
         for x0 in (-1.0, -0.3, 0.0, 0.7, 1.0):       # the objective is flat on the feasible segment
             x = np.zeros(5); x[0] = x0
             assert _objective(x, z[:k].astype(float), y[:k].astype(float)) == _objective(actions[k], z[:k].astype(float), y[:k].astype(float))
+
+
+def test_scipy_oracle_norms_agree_where_they_must():
+    """d = 1: the three unit balls coincide and the optimum is a clipped weighted median -- pins the LP / SLSQP
+    restatements of exact_ftl.py:83-105 against a closed form (including rows outside the ball and real labels)."""
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 7, 30):
+        z = rng.standard_normal((k, 1)) * 2.0
+        y = rng.standard_normal(k)
+        want = XS.weighted_median_d1(z, y)
+        for norm in XS.NORMS:
+            got, x = XS.solve(z, y, norm)
+            assert abs(got - want) <= 1e-7 * max(1.0, want), (k, norm, got, want)
+            assert abs(x[0]) <= 1.0 + 1e-9
+    # d > 1: l1 ball inside l2 ball inside linf ball -> optimal values are ordered the other way round
+    z = rng.standard_normal((25, 3)); y = rng.standard_normal(25)
+    f1, f2, fi = (XS.solve(z, y, n)[0] for n in ("l1", "l2", "linf"))
+    assert fi <= f2 + 1e-6 and f2 <= f1 + 1e-6

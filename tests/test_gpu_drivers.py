@@ -197,28 +197,9 @@ def _obj(x, z, y):
 
 
 def _scipy_opt(z, y, norm):
-    """Optimal value of min_{||x||_p<=1} 0.5*sum|z x - y| from an independent solver (HiGHS LP / SLSQP)."""
-    from scipy.optimize import linprog, minimize
-    k, d = z.shape
-    if norm == "linf":
-        c = np.concatenate([np.zeros(d), 0.5 * np.ones(k)])
-        A = np.block([[z, -np.eye(k)], [-z, -np.eye(k)]])
-        r = linprog(c, A_ub=A, b_ub=np.concatenate([y, -y]), bounds=[(-1, 1)] * d + [(0, None)] * k, method="highs")
-        return r.fun
-    if norm == "l1":
-        c = np.concatenate([np.zeros(2 * d), 0.5 * np.ones(k)])
-        A = np.block([[z, -z, -np.eye(k)], [-z, z, -np.eye(k)], [np.ones((1, 2 * d)), np.zeros((1, k))]])
-        r = linprog(c, A_ub=A, b_ub=np.concatenate([y, -y, [1.0]]), bounds=[(0, None)] * (2 * d + k), method="highs")
-        return r.fun
-    cons = [{"type": "ineq", "fun": lambda v: v[d:] - (z @ v[:d] - y)}, {"type": "ineq", "fun": lambda v: v[d:] + (z @ v[:d] - y)},
-            {"type": "ineq", "fun": lambda v: 1.0 - v[:d] @ v[:d]}]
-    best = np.inf
-    for x0 in (np.zeros(d), np.full(d, 0.2), -np.full(d, 0.2)):
-        v0 = np.concatenate([x0, np.abs(z @ x0 - y) + 0.1])
-        r = minimize(lambda v: 0.5 * v[d:].sum(), v0, constraints=cons, method="SLSQP", options={"maxiter": 1000, "ftol": 1e-13})
-        x = r.x[:d] / max(1.0, np.linalg.norm(r.x[:d]))
-        best = min(best, _obj(x, z, y))
-    return best
+    """Optimal value from the scipy restatement of the reference's program (oracle/exact_ftl_scipy.py)."""
+    from oracle import exact_ftl_scipy as XS
+    return XS.solve(z, y, norm)[0]
 
 
 @pytest.mark.parametrize("norm", ["l2", "linf", "l1"])

@@ -235,11 +235,19 @@ struct AsyncTile {
     // rows per register group: smallest R | kAT with R*D*ES a multiple of 16
     static constexpr int RG = ((D * ES) % 16 == 0) ? 1 : (((2 * D * ES) % 16 == 0) ? 2 : 4);
     static constexpr int GV = RG * D * ES / 16;                   // uint4 per row group
+    // copy loop: GS lanes (a power of two >= NP) walk one sequence's pieces, 32/GS sequences per instruction, so a
+    // lane's piece index, z-or-y choice and strides are constants of the lane (no per-piece index arithmetic)
+    static constexpr int GS = NP <= 2 ? 2 : (NP <= 4 ? 4 : (NP <= 8 ? 8 : (NP <= 16 ? 16 : 32)));
+    static constexpr int SPI = 32 / GS;
+    static_assert(NP <= 32, "tile record too wide for one copy group");
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -264,15 +272,20 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
     unsigned char* wsm = smem_raw + (size_t)wib * 2 * L::STAGE;
     const int ntiles = (int)(T / kAT);
 
+    const int cg = lane / L::GS, coff = lane % L::GS;              // this lane's sequence slot and piece in the copy loop
+    const bool cz = coff < L::ZB / 16, cvalid = coff < L::NP;
+    const int ctile = cz ? kAT * D * L::ES : kAT * L::ES;           // bytes per tile of this lane's piece stream
+    const int64_t cstep = (int64_t)L::SPI * (cz ? T * D * L::ES : T * L::ES);     // bytes between copy instructions
+    const unsigned char* csrc = cz ? zw + (int64_t)cg * T * D * L::ES + coff * 16
+                                   : yw + (int64_t)cg * T * L::ES + (coff - L::ZB / 16) * 16;
+    const uint32_t cdst = (uint32_t)__cvta_generic_to_shared(wsm) + cg * L::REC + coff * 16;
     auto stage_tile = [&](int tile, int st) {
-        unsigned char* dst = wsm + st * L::STAGE;
-        const int total = nseq * L::NP;
-        for (int pidx = lane; pidx < total; pidx += 32) {
-            const int s = pidx / L::NP, off = pidx - s * L::NP;
-            const unsigned char* src = (off < L::ZB / 16)
-                ? zw + ((int64_t)s * T + (int64_t)tile * kAT) * D * L::ES + off * 16
-                : yw + ((int64_t)s * T + (int64_t)tile * kAT) * L::ES + (off - L::ZB / 16) * 16;
-            cp_async16(dst + s * L::REC + off * 16, src);
+        const unsigned char* src = csrc + (int64_t)tile * ctile;
+        uint32_t dst = cdst + st * L::STAGE;
+#pragma unroll
+        for (int i = 0; i < L::GS; ++i) {
+            if (cvalid && i * L::SPI + cg < nseq) cp_async16_s(dst, src);
+            src += cstep; dst += L::SPI * L::REC;
         }
         cp_async_commit();
     };

@@ -12,16 +12,28 @@
 
 namespace oco {
 
-__global__ void stats_finalize_kernel(const double* __restrict__ partials, int nblocks, int A, int64_t n_runs,
-                                      double* __restrict__ stats) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= A) return;
+// One 256-thread block per variant; thread l folds chunks l, l + 256, ... in order, then a fixed shared-memory
+// tree: the association order depends only on (nblocks), so the statistics are reproducible run to run.
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const double* __restrict__ partials, int nblocks, int A,
+                                                             int64_t n_runs, double* __restrict__ stats) {
+    __shared__ double sm[3][256];
+    const int a = blockIdx.x, l = threadIdx.x;
     double m = -__longlong_as_double(0x7ff0000000000000LL), s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = l; b < nblocks; b += 256) {
         const double* o = partials + ((int64_t)b * A + a) * 3;
         m = fmax(m, o[0]); s1 += o[1]; s2 += o[2];
     }
-    stats[a * 4 + 0] = m; stats[a * 4 + 1] = s1; stats[a * 4 + 2] = s2; stats[a * 4 + 3] = (double)n_runs;
+    sm[0][l] = m; sm[1][l] = s1; sm[2][l] = s2;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (l < w) {
+            sm[0][l] = fmax(sm[0][l], sm[0][l + w]);
+            sm[1][l] = sm[1][l] + sm[1][l + w];
+            sm[2][l] = sm[2][l] + sm[2][l + w];
+        }
+        __syncthreads();
+    }
+    if (l == 0) { stats[a * 4 + 0] = sm[0][0]; stats[a * 4 + 1] = sm[1][0]; stats[a * 4 + 2] = sm[2][0]; stats[a * 4 + 3] = (double)n_runs; }
 }
 
 __global__ void ftrl_scale_table_kernel(double* __restrict__ tab, const Etas eta0, int64_t T, int A) {
@@ -89,7 +101,7 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
 }
 
 cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, int64_t n_runs, double* stats, cudaStream_t st) {
-    stats_finalize_kernel<<<(A + 63) / 64, 64, 0, st>>>(partials, nblocks, A, n_runs, stats);
+    stats_finalize_kernel<<<A, 256, 0, st>>>(partials, nblocks, A, n_runs, stats);
     return cudaGetLastError();
 }
 

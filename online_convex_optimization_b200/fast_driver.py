@@ -69,7 +69,9 @@ def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicat
                                            dtype=torch.float32)
         alg = engine.simulate_batch_device(z, y, [0, 1], [SQRT2, SQRT2], compute=compute)
         smart, _ = engine.smart_batch_device(z, y, thresholds, [SQRT2, SQRT2])
-        out = torch.cat([alg, smart], dim=1).cpu().numpy()
+        # stays on the device, nothing synchronises here: the caller gathers every horizon with one copy at the end,
+        # so the kernels of all horizons run back to back
+        return torch.cat([alg, smart], dim=1).reshape(runs, replicates, 4)
     else:
         # foreign stream builders: sample on the host exactly as the reference does, batch the rest
         zs, ys = [], []
@@ -99,9 +101,11 @@ def evaluate_stream_with_stats(
     """fast_driver.py:71-127 -- mean regret and 95 % CI per algorithm at each T.
     compute="f32" plays FTRL / FTL with the float32-state semantics of algorithms.py (driver.py twin)."""
     by_T = {k: [] for k in ALGO_KEYS}
-    for T in T_grid:
-        T_int = int(T)
-        reg = _regrets_for_T(stream_builder, T_int, float(g_emp[T_int]), runs, replicates, base_seed, compute)
+    pending = [_regrets_for_T(stream_builder, int(T), float(g_emp[int(T)]), runs, replicates, base_seed, compute)
+               for T in T_grid]                     # device tensors (enqueued) or host arrays
+    for reg in pending:
+        if not isinstance(reg, np.ndarray):
+            reg = reg.cpu().numpy()                 # first call waits for the stream; the rest are already there
         for ki, k in enumerate(ALGO_KEYS):
             # fast_driver.py:113-114: per run, float(np.mean(list of replicate regrets))
             by_T[k].append([float(np.mean([float(v) for v in reg[run, :, ki]])) for run in range(runs)])

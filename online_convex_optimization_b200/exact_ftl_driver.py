@@ -15,6 +15,7 @@ import numpy as np
 from numpy.typing import NDArray
 
 from . import engine
+from ._lib import FAM_IID, FAM_NOISY
 from .exact_ftl import ExactFTLNoClip
 from .fast_algorithms import _rng  # noqa: F401  (exact_ftl_driver.py:23 imports it)
 from .sequence_generation import CASES, REPLICATES_BY_TITLE, RUNS_BY_TITLE
@@ -83,13 +84,25 @@ def evaluate_stream_with_stats(stream_builder: Callable[..., Callable], T_grid: 
     samplers = [stream_builder(run_seed=cfg.base_seed + 2025 * (run + 1)) for run in range(runs)]
     for T in T_grid:
         T_int = int(T)
-        zs, ys = [], []
-        for s in samplers:
-            for rep in range(replicates):
-                z, y, _ = s(T_int, rep=rep)
-                zs.append(z)
-                ys.append(y)
-        ftrl, ftl = _exact_and_ftrl(np.stack(zs), np.stack(ys))
+        spec = getattr(samplers[0], "spec", None) if samplers else None
+        if spec is not None:
+            # the twin's own stream builders: one generator launch for all runs x replicates of this horizon
+            keys = None
+            if spec["family"] in (FAM_IID, FAM_NOISY):
+                keys = np.array([[s.spec["run_seed"], s.spec["stream0"] + rep] for s in samplers for rep in range(replicates)],
+                                dtype=np.uint64)
+            zb, yb = engine.gen_sequences(spec["family"], runs * replicates, T_int, spec["d"], keys=keys, p_flip=spec["p"],
+                                          block_len=spec.get("block_len", 20), dtype=np.float32)
+        else:
+            # foreign stream builders: sample on the host exactly as the reference does
+            zs, ys = [], []
+            for s in samplers:
+                for rep in range(replicates):
+                    z, y, _ = s(T_int, rep=rep)
+                    zs.append(z)
+                    ys.append(y)
+            zb, yb = np.stack(zs), np.stack(ys)
+        ftrl, ftl = _exact_and_ftrl(zb, yb)
         vals = {"FTRL": ftrl.reshape(runs, replicates), "FTL (exact)": ftl.reshape(runs, replicates)}
         for label in algo_labels:
             by_T[label].append([float(np.mean([float(v) for v in vals[label][run]])) for run in range(runs)])

@@ -431,6 +431,14 @@ OCO_API int oco_gen_sequences(int family, uint64_t key_a, uint64_t key_c0, const
     return OCO_OK;
 }
 
+// Touch one byte per page of an output buffer the library is about to overwrite anyway.
+static void prefault_output(void* p, size_t bytes) {
+    if (!p || !bytes) return;
+    volatile unsigned char* c = reinterpret_cast<volatile unsigned char*>(p);
+    for (size_t off = 0; off < bytes; off += 4096) c[off] = 0;
+    c[bytes - 1] = 0;
+}
+
 OCO_API int oco_gen_sequences_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
                            int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
                            int out_dtype, void* z, void* y, int device) {
@@ -445,6 +453,7 @@ OCO_API int oco_gen_sequences_host(int family, uint64_t key_a, uint64_t key_c0, 
         cudaError_t e1 = zd.alloc((size_t)B * T * d * es, st), e2 = yd.alloc((size_t)B * T * es, st);
         if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
         if (!rc) rc = oco_gen_sequences(family, key_a, key_c0, keys, B, T, d, p_flip, block_len, out_dtype, zd.p, yd.p, st);
+        if (!rc) { prefault_output(z, (size_t)B * T * d * es); prefault_output(y, (size_t)B * T * es); }   // while the fill runs
         if (!rc && (cudaMemcpyAsync(z, zd.p, (size_t)B * T * d * es, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                     cudaMemcpyAsync(y, yd.p, (size_t)B * T * es, cudaMemcpyDeviceToHost, st) != cudaSuccess))
             rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");
@@ -484,14 +493,6 @@ OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const 
                     stats ? part.as<double>() : nullptr, st));
     if (stats) CU(launch_stats_finalize(part.as<double>(), nblocks, A, B, stats, st));
     return OCO_OK;
-}
-
-// Touch one byte per page of an output buffer the library is about to overwrite anyway.
-static void prefault_output(void* p, size_t bytes) {
-    if (!p || !bytes) return;
-    volatile unsigned char* c = reinterpret_cast<volatile unsigned char*>(p);
-    for (size_t off = 0; off < bytes; off += 4096) c[off] = 0;
-    c[bytes - 1] = 0;
 }
 
 OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,

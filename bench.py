@@ -426,7 +426,8 @@ def main():
         engine.release_scratch(local)
         extras = {}
         try:
-            w5 = dict(WORKLOADS["c5"]); w5["trials"] = 250_000
+            # 378,880 = 4 x 94,720 = 5 x 75,776: whole waves of resident threads at either 5 or 4 CTAs per SM
+            w5 = dict(WORKLOADS["c5"]); w5["trials"] = 378_880
             for _ in range(2):
                 engine.regret_sweep_device("gpath", w5["trials"], w5["T"], w5["d"], w5["alg"], w5["eta"])
             torch.cuda.synchronize()

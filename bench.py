@@ -167,7 +167,8 @@ def run_streamed(args, wl, *, emit=True, init_dist=True):
     # e2e: host buffers (pinned) through the host API, PCIe copies inside the timed region, bounded sample
     nb = min(B, 512)
     zh = z[:nb].cpu().pin_memory().numpy(); yh = y[:nb].cpu().pin_memory().numpy()
-    engine.simulate_batch(zh[:64], yh[:64], wl["alg"], wl["eta"], comparator=mode, device=local)
+    # warm-up at the timed size: the first full-size call grows the library's stream-ordered pool (device chunk buffers)
+    engine.simulate_batch(zh, yh, wl["alg"], wl["eta"], comparator=mode, device=local)
     barrier()
     t0 = time.perf_counter()
     out = engine.simulate_batch(zh, yh, wl["alg"], wl["eta"], comparator=mode, device=local)

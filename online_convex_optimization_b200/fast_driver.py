@@ -100,9 +100,18 @@ def evaluate_stream_with_stats(
 ) -> Stats:
     """fast_driver.py:71-127 -- mean regret and 95 % CI per algorithm at each T.
     compute="f32" plays FTRL / FTL with the float32-state semantics of algorithms.py (driver.py twin)."""
+    return _finish_case(_enqueue_case(stream_builder, T_grid, g_emp, runs, replicates, base_seed, compute), runs)
+
+
+def _enqueue_case(stream_builder, T_grid, g_emp, runs, replicates, base_seed, compute="f64") -> list:
+    """Launch every horizon of one case; returns device tensors (enqueued, not synchronised) or host arrays."""
+    return [_regrets_for_T(stream_builder, int(T), float(g_emp[int(T)]), runs, replicates, base_seed, compute)
+            for T in T_grid]
+
+
+def _finish_case(pending: list, runs: int) -> Stats:
+    """Gather the per-sequence regrets of one case and form the reference's statistics (fast_driver.py:113-125)."""
     by_T = {k: [] for k in ALGO_KEYS}
-    pending = [_regrets_for_T(stream_builder, int(T), float(g_emp[int(T)]), runs, replicates, base_seed, compute)
-               for T in T_grid]                     # device tensors (enqueued) or host arrays
     for reg in pending:
         if not isinstance(reg, np.ndarray):
             reg = reg.cpu().numpy()                 # first call waits for the stream; the rest are already there
@@ -126,11 +135,11 @@ def run_experiment(cfg: ExperimentConfig = None) -> dict:
     """fast_driver.main (fast_driver.py:201-220) without the plotting."""
     cfg = cfg or ExperimentConfig()
     g_emp = empirical_worst_case_thresholds(cfg.T_grid, runs=cfg.g_runs, base_seed=cfg.base_seed)
-    stats_by_case: Dict[str, Stats] = {}
-    for title, builder in CASES.items():
-        stats_by_case[title] = evaluate_stream_with_stats(
-            builder, cfg.T_grid, g_emp, runs=RUNS_BY_TITLE.get(title, 1), replicates=REPLICATES_BY_TITLE.get(title, 1),
-            base_seed=cfg.base_seed, stream_name=title)
+    # all four cases are enqueued before the first gather, so the GPU never waits for the host-side statistics
+    pending = {title: _enqueue_case(builder, cfg.T_grid, g_emp, RUNS_BY_TITLE.get(title, 1),
+                                    REPLICATES_BY_TITLE.get(title, 1), cfg.base_seed)
+               for title, builder in CASES.items()}
+    stats_by_case: Dict[str, Stats] = {title: _finish_case(p, RUNS_BY_TITLE.get(title, 1)) for title, p in pending.items()}
     return {"T_grid": [int(t) for t in cfg.T_grid], "g_emp": g_emp, "stats_by_case": stats_by_case}
 
 

@@ -116,8 +116,10 @@ def _finish_case(pending: list, runs: int) -> Stats:
         if not isinstance(reg, np.ndarray):
             reg = reg.cpu().numpy()                 # first call waits for the stream; the rest are already there
         for ki, k in enumerate(ALGO_KEYS):
-            # fast_driver.py:113-114: per run, float(np.mean(list of replicate regrets))
-            by_T[k].append([float(np.mean([float(v) for v in reg[run, :, ki]])) for run in range(runs)])
+            # fast_driver.py:113-114: per run, float(np.mean(list of replicate regrets)) -- the row-wise mean of a
+            # C-contiguous (runs, replicates) array runs the same pairwise add.reduce per row, bit for bit
+            # (checked against the reference's own statistics by test_fast_driver_full_default_workload)
+            by_T[k].append(np.ascontiguousarray(reg[:, :, ki]).mean(axis=1).tolist())
     stats: Stats = {}
     for k in ALGO_KEYS:
         means, cis = [], []

@@ -42,22 +42,26 @@ def _task_vector(run_seed: int, stream_id: int, d: int) -> np.ndarray:
 
 def make_random_iid_stream(*, d: int = 5, run_seed: int = 0):
     """sequence_generation.py:54-70."""
-    u = _task_vector(run_seed, 11, d)
+    u_cache = []                                  # u is formed on first use: the batched drivers never ask for it
 
     def sample(T: int, rep: int = 0):
+        if not u_cache:
+            u_cache.append(_task_vector(run_seed, 11, d))
         z, y = engine.gen_sequences(FAM_IID, 1, T, d, key_a=run_seed, key_c0=13 + rep, dtype=np.float32)
-        return z[0], y[0], u
+        return z[0], y[0], u_cache[0]
     sample.spec = {"family": FAM_IID, "run_seed": run_seed, "d": d, "p": -1.0, "stream0": 13}
     return sample
 
 
 def make_noisy_iid_stream(*, p: float, d: int = 5, run_seed: int = 0):
     """sequence_generation.py:72-90."""
-    u = _task_vector(run_seed, 21, d)
+    u_cache = []
 
     def sample(T: int, rep: int = 0):
+        if not u_cache:
+            u_cache.append(_task_vector(run_seed, 21, d))
         z, y = engine.gen_sequences(FAM_NOISY, 1, T, d, key_a=run_seed, key_c0=23 + rep, p_flip=p, dtype=np.float32)
-        return z[0], y[0], u
+        return z[0], y[0], u_cache[0]
     sample.spec = {"family": FAM_NOISY, "run_seed": run_seed, "d": d, "p": float(p), "stream0": 23}
     return sample
 

@@ -284,6 +284,20 @@ def ncu_utilisation(kernel: str):
         return None
 
 
+def hbm_view(traffic_bytes_per_step, ms_per_step):
+    """The same kernel against the HBM roofline (why it is NOT the bound): DRAM bytes per step from the committed ncu
+    capture divided by the measured step time, against MEASURED_PEAKS.json hbm_gbs."""
+    if not traffic_bytes_per_step:
+        return None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        peak = 6650.0
+    gbs = traffic_bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "note": "slab traffic only; inputs are generated on chip, so HBM is not the limiter of this kernel"}
+
+
 def _quiet_stdout():
     """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.
     Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
@@ -413,7 +427,8 @@ def main():
                          "traffic": ncu_traffic(kname, float(B) * A * T), "kernel": kname,
                          "algorithmic_ops_per_trajectory_step": alg_ops,
                          "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)",
-                         "ncu": ncu_utilisation(kname)},
+                         "ncu": ncu_utilisation(kname),
+                         "hbm_view": hbm_view(ncu_traffic(kname, float(B) * A * T), ms / args.steps)},
             "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
                              "mean_regret_per_variant": [float(v) for v in st[:, 1] / np.maximum(st[:, 3], 1)]},
         }

@@ -173,11 +173,30 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
                           const int* alg_flag, const double* eta0, int A,
                           double* regret, double* cum_loss, double* comp_loss, double* stats, int device);
 
+/* Same with an explicit comparator_mode (the entry points above are OCO_COMPARATOR_TWO_PASS, bit-exact for d <= 5):
+ * OCO_COMPARATOR_LINEAR applies to the g-path family with 2 <= d <= 5 (other shapes ignore it and stay exact):
+ * rows are regenerated in registers instead of being parked in a scratch slab (no DRAM traffic) and the
+ * comparator loss of fast_algorithms.py:113-114 is T/2 - ||theta_T|| -- valid because the kernel verifies
+ * sign(q_t - y_t) == -y_t on every step; a sequence that ever violates it takes the literal second pass.
+ * cum_loss stays bit-exact; regret / comp_loss agree with the reference to 1e-12 * max(1, cum_loss). */
+OCO_API int oco_regret_sweep_mode(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                          int64_t B, int64_t T, int d, double p_flip,
+                          const int* alg_flag, const double* eta0, int A,
+                          double* regret, double* cum_loss, double* comp_loss, double* stats,
+                          int comparator_mode, void* stream);
+OCO_API int oco_regret_sweep_mode_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                               int64_t B, int64_t T, int d, double p_flip,
+                               const int* alg_flag, const double* eta0, int A,
+                               double* regret, double* cum_loss, double* comp_loss, double* stats,
+                               int comparator_mode, int device);
+
 /* ---- fast_algorithms.empirical_worst_case_thresholds (fast_algorithms.py:211-247) for runs
  * [run_lo, run_lo + n_runs): g_max[i] = max(0, max_r regret_FTRL(eta0)) on g-path sequences of
  * length T_grid[i]; stats [nT*4] as above (may be NULL).  d <= 5 (the reference uses 5). */
 OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
                      int d, double eta0, double* g_max, double* stats, int device);
+OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
+                          int d, double eta0, double* g_max, double* stats, int comparator_mode, int device);
 
 /* ---- known-answer probes of the device generator (tests): what = 0 raw uint64, 1 standard
  * normals, 2 random() doubles, 3 choice([-1,1]) labels, 4 SeedSequence state words, 5 log1p(-U);

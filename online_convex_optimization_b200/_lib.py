@@ -35,6 +35,9 @@ SIGNATURES = {
     "oco_regret_sweep": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "oco_regret_sweep_host": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i], _i),
     "oco_g_sweep_host": ([_vp, _i, _u64, _i64, _u64, _i, _dbl, _vp, _vp, _i], _i),
+    "oco_regret_sweep_mode": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "oco_regret_sweep_mode_host": ([_i, _u64, _u64, _vp, _i64, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i], _i),
+    "oco_g_sweep_mode_host": ([_vp, _i, _u64, _i64, _u64, _i, _dbl, _vp, _vp, _i, _i], _i),
     "oco_rng_probe_host": ([_i, _u64, _u64, _u64, _i64, _i64, _vp, _i], _i),
     "oco_release_scratch": ([_i], _i),
     "oco_fp64_peak_probe_host": ([_i, C.POINTER(_dbl)], _i),

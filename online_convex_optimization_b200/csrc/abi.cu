@@ -469,6 +469,16 @@ OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const 
                      int64_t B, int64_t T, int d, double p_flip,
                      const int* alg_flag, const double* eta0, int A,
                      double* regret, double* cum_loss, double* comp_loss, double* stats, void* stream) {
+    return oco_regret_sweep_mode(family, key_a, key_c0, keys, B, T, d, p_flip, alg_flag, eta0, A, regret, cum_loss, comp_loss,
+                                 stats, OCO_COMPARATOR_TWO_PASS, stream);
+}
+
+OCO_API int oco_regret_sweep_mode(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                          int64_t B, int64_t T, int d, double p_flip,
+                          const int* alg_flag, const double* eta0, int A,
+                          double* regret, double* cum_loss, double* comp_loss, double* stats, int comparator_mode, void* stream) {
+    if (comparator_mode != OCO_COMPARATOR_TWO_PASS && comparator_mode != OCO_COMPARATOR_LINEAR)
+        return fail(OCO_ERR_VALUE, "comparator_mode must be OCO_COMPARATOR_TWO_PASS or OCO_COMPARATOR_LINEAR");
     if (B < 0 || T < 0 || d < 1) return fail(OCO_ERR_VALUE, "need B >= 0, T >= 0, d >= 1");
     if (A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need 1 <= A <= %d (got %d)", OCO_MAX_VARIANTS, A);
     if (int rc = check_family(family, d, true)) return rc;
@@ -490,7 +500,7 @@ OCO_API int oco_regret_sweep(int family, uint64_t key_a, uint64_t key_c0, const 
     const int nblocks = sweep_gpath_blocks(B);
     if (stats) CU(part.alloc(sizeof(double) * 3 * (size_t)nblocks * A, st));
     CU(launch_sweep(family, key_a, key_c0, kd, T, B, d, p_flip, plan, tab.as<double>(), regret, cum_loss, comp_loss,
-                    stats ? part.as<double>() : nullptr, st));
+                    stats ? part.as<double>() : nullptr, comparator_mode, st));
     if (stats) CU(launch_stats_finalize(part.as<double>(), nblocks, A, B, stats, st));
     return OCO_OK;
 }
@@ -499,6 +509,14 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
                           int64_t B, int64_t T, int d, double p_flip,
                           const int* alg_flag, const double* eta0, int A,
                           double* regret, double* cum_loss, double* comp_loss, double* stats, int device) {
+    return oco_regret_sweep_mode_host(family, key_a, key_c0, keys, B, T, d, p_flip, alg_flag, eta0, A, regret, cum_loss,
+                                      comp_loss, stats, OCO_COMPARATOR_TWO_PASS, device);
+}
+
+OCO_API int oco_regret_sweep_mode_host(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys,
+                               int64_t B, int64_t T, int d, double p_flip,
+                               const int* alg_flag, const double* eta0, int A,
+                               double* regret, double* cum_loss, double* comp_loss, double* stats, int comparator_mode, int device) {
     if (B < 0 || A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need B >= 0 and 1 <= A <= %d", OCO_MAX_VARIANTS);
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -512,8 +530,8 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
         if (comp_loss) ok = ok && pd.alloc(n, st) == cudaSuccess;
         if (stats) ok = ok && sd.alloc(sizeof(double) * 4 * A, st) == cudaSuccess;
         if (!ok) rc = fail(OCO_ERR_RUNTIME, "device allocation failed");
-        if (!rc) rc = oco_regret_sweep(family, key_a, key_c0, keys, B, T, d, p_flip, alg_flag, eta0, A,
-                                       rd.as<double>(), cd.as<double>(), pd.as<double>(), sd.as<double>(), st);
+        if (!rc) rc = oco_regret_sweep_mode(family, key_a, key_c0, keys, B, T, d, p_flip, alg_flag, eta0, A,
+                                            rd.as<double>(), cd.as<double>(), pd.as<double>(), sd.as<double>(), comparator_mode, st);
         if (!rc) {
             // The sweep is now running; fault in the caller's (typically fresh, pageable) output pages meanwhile.
             // First-touch faults on 72 MB cost ~13 ms when they happen inside the device-to-host copy instead.
@@ -534,6 +552,11 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
 
 OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
                      int d, double eta0, double* g_max, double* stats, int device) {
+    return oco_g_sweep_mode_host(T_grid, nT, run_lo, n_runs, base_seed, d, eta0, g_max, stats, OCO_COMPARATOR_TWO_PASS, device);
+}
+
+OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
+                          int d, double eta0, double* g_max, double* stats, int comparator_mode, int device) {
     if (!T_grid || !g_max || nT < 0) return fail(OCO_ERR_VALUE, "T_grid / g_max must not be NULL");
     if (n_runs < 0) return fail(OCO_ERR_VALUE, "n_runs must be >= 0");
     DeviceGuard g; if (int rc = g.set(device)) return rc;
@@ -546,8 +569,8 @@ OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int
         const int flag = OCO_ALG_FTRL;
         for (int i = 0; i < nT && !rc; ++i) {
             if (T_grid[i] < 0) { rc = fail(OCO_ERR_VALUE, "T_grid[%d] < 0", i); break; }
-            rc = oco_regret_sweep(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T_grid[i], d, -1.0, &flag, &eta0, 1,
-                                  nullptr, nullptr, nullptr, sd.as<double>() + 4 * i, st);
+            rc = oco_regret_sweep_mode(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T_grid[i], d, -1.0, &flag, &eta0, 1,
+                                       nullptr, nullptr, nullptr, sd.as<double>() + 4 * i, comparator_mode, st);
         }
         if (!rc && nT > 0 && cudaMemcpyAsync(hs.data(), sd.p, sizeof(double) * 4 * nT, cudaMemcpyDeviceToHost, st) != cudaSuccess)
             rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");

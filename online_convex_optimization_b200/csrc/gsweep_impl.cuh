@@ -1,0 +1,443 @@
+// gsweep_impl.cuh -- the g-path sweep for d > 1 with the single-pass ("linear") comparator:
+// generate + play + compare with NO second pass over the rows and (by default) NO scratch traffic.
+//
+//   gsweep_kernel<D, NFTL, NF>: one thread per seeded sequence of fast_algorithms.py:231-239
+//   (z = standard_normal((T, d)) clipped to the unit ball, y = choice([-1, 1], T)), persistent CTAs.
+//
+//   numpy draws the T labels AFTER all T*d normals from the same PCG64 stream, and the ziggurat
+//   consumes a data-dependent number of raw draws, so the label cursor is only known once every
+//   normal of the sequence has been (at least) counted.  sweep_kernel (sweep_impl.cuh) therefore
+//   parks the rows in an HBM slab (8*d bytes written, 16*d read per step).  Here instead:
+//     pass 1  COUNT: walk the stream once doing only what decides how many raws each normal
+//             consumes (PCG64 step + output + the `rabs < ki[idx]` test; the wedge / tail tests
+//             only for the 0.85 % of draws that fail it) -- integer work, no stores;
+//     pass 2  PLAY:  re-seed, regenerate every row in registers right before it is played, with
+//             the labels drawn from the cursor pass 1 found.
+//   The first `t_split` rows can optionally go through a slab instead (generated once in pass 1,
+//   streamed back in pass 2): t_split = 0 is the pure regenerating kernel (zero DRAM bytes per
+//   step), t_split = T the pure slab kernel; the launcher picks it (OCO_GSWEEP_SLAB_FRAC).
+//
+//   Comparator without a second pass (fast_algorithms.py:113-114, 69-76).  Rows have ||z_t|| <= 1
+//   (clipped, up to 2 ulp) and y_t = +-1.  Whenever the played q_t = z_t.x_t satisfies
+//   sign(q_t - y_t) == -y_t and q_t != y_t -- i.e. |q_t| < 1, checked on EVERY step below -- the
+//   gradient is g_t = -0.5*y_t, so theta_T = -0.5 * sum_t y_t z_t =: -0.5 v holds bit for bit (the
+//   same additions in the same order, scaled by a power of two).  The comparator a = -theta_T/||theta_T||
+//   = v/||v|| has |z_t.a| <= 1, hence 0.5|z_t.a - y_t| = 0.5(1 - y_t z_t.a) and
+//        comp = 0.5 (T - a.v) = T/2 - ||theta_T||,        regret = (cum - T/2) + ||theta_T||.
+//   cum (the played loss) is accumulated exactly as the reference does, so only comp differs from
+//   the reference's sequential sum, by that sum's own rounding noise: |d regret| <= 1e-12 *
+//   max(1, cum) (north_star's tolerance for d > 1; tests/test_gpu_parity.py states it).  A sequence
+//   for which the per-step check ever fails (never observed; needs |q_t| >= 1) is re-evaluated by
+//   the literal second pass in gsweep_exact_comp below, so the kernel never returns an unchecked
+//   shortcut.
+//
+//   All arithmetic of the played trajectory is the bit-exact restatement of oco_device.cuh
+//   (-fmad=false, reference order); theta is kept doubled (theta2 = 2*theta: the gradient step is a
+//   sign flip + DADD, the scales are halved once per step -- power-of-two scalings commute with
+//   rounding).
+#pragma once
+#include "sweep_impl.cuh"
+
+namespace oco {
+
+// ---------------------------------------------------------------- generator, streamlined fast path
+struct ZigTab2 {                 // shared memory, 6 KB
+    ulonglong2 wk[256];          // .x = bits of wi[idx], .y = ki[idx] | 0x4330000000000000 (one LDS.128 per draw)
+    double fi[256];
+};
+
+__device__ __forceinline__ void zig_tab2_load(ZigTab2& s) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        s.wk[i] = make_ulonglong2(g_zig_wi[i], g_zig_ki[i] | 0x4330000000000000ULL);
+        s.fi[i] = __longlong_as_double((long long)g_zig_fi[i]);
+    }
+    __syncthreads();
+}
+
+// Top of numpy's random_standard_normal loop for one raw r: candidate x, its layer and magnitude;
+// returns the fast-accept test rabs < ki[idx].  mag = rabs | 2^52-exponent: the same word serves the
+// exact int -> double conversion (one DADD) and, against the pre-or'ed ki, the comparison.
+__device__ __forceinline__ bool zig_try(const ZigTab2& tb, uint64_t r, double& x, int& idx, uint64_t& mag) {
+    idx = (int)(r & 0xff);
+    mag = ((r >> 9) & 0x000fffffffffffffULL) | 0x4330000000000000ULL;
+    const ulonglong2 wk = tb.wk[idx];
+    const int sgn = (int)(((uint32_t)r << 23) & 0x80000000u);                    // bit 8 of r -> sign bit
+    const double w = __hiloint2double((int)(wk.x >> 32) ^ sgn, (int)(uint32_t)wk.x);   // (+-wi): (-a)*b == -(a*b)
+    x = (__longlong_as_double((long long)mag) - 4503599627370496.0) * w;
+    return mag < wk.y;
+}
+// the test alone (count pass): no float work
+__device__ __forceinline__ bool zig_test(const ZigTab2& tb, uint64_t r, int& idx, uint64_t& mag) {
+    idx = (int)(r & 0xff);
+    mag = ((r >> 9) & 0x000fffffffffffffULL) | 0x4330000000000000ULL;
+    return mag < tb.wk[idx].y;
+}
+
+// tail sampler (idx == 0, 0.028 % of draws): out of line, state by value
+struct ZigTailRet { double x; uint64_t hi, lo; };
+static __device__ __noinline__ ZigTailRet zig_tail(uint64_t s_hi, uint64_t s_lo, uint64_t inc_hi, uint64_t inc_lo, uint64_t rabs) {
+    Pcg64 s; s.hi = s_hi; s.lo = s_lo;
+    PcgInc inc; inc.hi = inc_hi; inc.lo = inc_lo;
+    ZigTailRet out;
+    for (;;) {
+        const double xx = -OCO_ZIG_INV_R * log1p_glibc_fma(-pcg_double(s, inc));
+        const double yy = -log1p_glibc_fma(-pcg_double(s, inc));
+        if (yy + yy > xx * xx) {
+            out.x = ((rabs >> 8) & 1) ? -(OCO_ZIG_R + xx) : OCO_ZIG_R + xx;
+            out.hi = s.hi; out.lo = s.lo;
+            return out;
+        }
+    }
+}
+
+// The wedge comparison yv < exp(arg) in double precision: only reached when the float bracket below cannot
+// decide (probability ~2e-5 per wedge test); out of line so that the caller stays small.
+static __device__ __noinline__ bool zig_wedge_exact(double yv, double arg) { return yv < exp(arg); }
+
+// Everything after a failed fast test, until a normal is accepted (numpy's for(;;) body from the
+// `if (idx == 0)` on, including the redraws).  The wedge comparison is bracketed with a float
+// exponential exactly as in rng_numpy.cuh::zig_slow (same decisions, see the comment there).
+// A warp enters this whenever ANY of its 32 lanes fails the fast test (24 % of the draws at warp level for
+// 0.85 % per lane), so it is written to be short: ~45 instructions for an accepted wedge candidate.
+#ifndef OCO_ZIG_SLOW_INLINE
+#define OCO_ZIG_SLOW_INLINE 1
+#endif
+#if OCO_ZIG_SLOW_INLINE
+#define OCO_ZIG_SLOW_ATTR __forceinline__
+#else
+#define OCO_ZIG_SLOW_ATTR __noinline__
+#endif
+static __device__ OCO_ZIG_SLOW_ATTR double zig_slow2(const ZigTab2& tb, Pcg64& s, const PcgInc& inc, int idx, uint64_t mag, double x) {
+    for (;;) {
+        if (idx == 0) {
+            const ZigTailRet o = zig_tail(s.hi, s.lo, inc.hi, inc.lo, mag & 0x000fffffffffffffULL);
+            s.hi = o.hi; s.lo = o.lo;
+            return o.x;
+        }
+        const double f1 = tb.fi[idx], f0 = tb.fi[idx - 1];
+        const double yv = (f0 - f1) * pcg_double(s, inc) + f1;
+        const double arg = -0.5 * x * x;
+        const double ef = (double)__expf((float)arg);
+        const bool sure_yes = yv < ef * (1.0 - 1e-5), sure_no = yv > ef * (1.0 + 1e-5);
+        bool accept = sure_yes;
+        if (!sure_yes && !sure_no) accept = zig_wedge_exact(yv, arg);
+        if (accept) return x;
+        const uint64_t r = pcg_next64(s, inc);              // rejected: a fresh attempt
+        if (zig_try(tb, r, x, idx, mag)) return x;
+    }
+}
+
+__device__ __forceinline__ double zig_normal2(const ZigTab2& tb, Pcg64& s, const PcgInc& inc) {
+    const uint64_t r = pcg_next64(s, inc);
+    double x; int idx; uint64_t mag;
+    if (zig_try(tb, r, x, idx, mag)) return x;
+    return zig_slow2(tb, s, inc, idx, mag, x);
+}
+// advance the stream past one normal (count pass)
+__device__ __forceinline__ void zig_skip2(const ZigTab2& tb, Pcg64& s, const PcgInc& inc) {
+    const uint64_t r = pcg_next64(s, inc);
+    int idx; uint64_t mag;
+    if (zig_test(tb, r, idx, mag)) return;
+    double x; zig_try(tb, r, x, idx, mag);
+    zig_slow2(tb, s, inc, idx, mag, x);
+}
+
+// one row of fast_algorithms.py:234-236: d normals, z *= 1.0 / max(||z||, 1.0)
+template <int D>
+__device__ __forceinline__ void gpath_row2(const ZigTab2& tb, Pcg64& s, const PcgInc& inc, double (&z)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = zig_normal2(tb, s, inc);
+    const double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+    const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
+}
+
+// ---------------------------------------------------------------- exact fallback (never taken on g-path data)
+// Literal second pass sum_t |z_t.a - y_t| for one sequence and one comparator a (fast_algorithms.py:69-76):
+// count pass for the label cursor, then regenerate rows and labels.
+template <int D>
+static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint64_t ka, int T, uint64_t kc, const double* a_in) {
+    const ZigTab2& tb = *tbp;
+    double a[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) a[j] = a_in[j];
+    Pcg64 s; PcgInc inc;
+    pcg_seed3(s, inc, ka, (uint64_t)T, kc);
+    Pcg64 s0 = s;
+    for (int n = 0; n < T * D; ++n) zig_skip2(tb, s, inc);
+    LabelCursor lab; lab.s = s; lab.cur = 0;
+    s = s0;
+    double C = 0.0;
+    for (int t = 0; t < T; ++t) {
+        double z[D];
+        gpath_row2<D>(tb, s, inc, z);
+        const double y = lab.next(t, inc);
+        C = C + fabs(dot_seq<D>(z, a) - y);
+    }
+    return C;
+}
+
+// ---------------------------------------------------------------- the kernel
+#ifndef OCO_GSWEEP_MIN_BLOCKS
+#define OCO_GSWEEP_MIN_BLOCKS 6
+#endif
+
+template <int D, int NFTL, int NF>
+__global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : 4)) gsweep_kernel(const SweepArgs p) {
+    static_assert(D >= 2 && D <= 8, "d = 1 has the exact one-pass comparator of sweep_kernel");
+    __shared__ ZigTab2 tb;
+    __shared__ double red[kSweepBlock / 32][3];
+    zig_tab2_load(tb);
+    const int T = p.T, A = p.plan.A, tid = threadIdx.x;
+    const int groups = p.plan.groups;
+    const int ts = p.t_split;                                   // rows [0, ts) go through the slab
+    double* __restrict__ zs = reinterpret_cast<double*>(p.slab_z) + (int64_t)blockIdx.x * ts * D * kSweepBlock + tid;
+
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t chunk = item / groups;
+        const int g = (int)(item - chunk * groups);
+        const bool active = chunk * kSweepBlock + tid < p.B;
+        const int64_t b = active ? chunk * kSweepBlock + tid : p.B - 1;   // idle lanes replay the last sequence
+        constexpr unsigned mask = 0xffffffffu;
+        const int nf = min(NF, p.plan.n_ftrl - g * NF);
+        const bool do_ftl = NFTL > 0 && g == 0 && p.plan.n_ftl > 0;
+        double reg_r[NF], reg_l = 0.0;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
+
+        {
+            const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
+            const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
+            Pcg64 s; PcgInc inc;
+            pcg_seed3(s, inc, ka, (uint64_t)T, kc);
+
+            // ---- pass 1a: rows [0, ts) generated once, parked in the slab ([t][j][thread], coalesced)
+            if (p.debug_phase != 2) {
+                double* __restrict__ zw = zs;
+                for (int t = 0; t < ts; ++t, zw += D * kSweepBlock) {
+                    double z[D];
+                    gpath_row2<D>(tb, s, inc, z);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) zw[j * kSweepBlock] = z[j];
+                }
+            }
+            const Pcg64 s_mid = s;                              // stream position of row ts
+            // ---- pass 1b: count the raws of rows [ts, T) (no float work on the fast path, no stores)
+            for (int t = ts; t < T; ++t) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) zig_skip2(tb, s, inc);
+            }
+            LabelCursor lab; lab.s = s; lab.cur = 0;            // choice([-1, 1], T) continues the stream here
+
+            // ---- pass 2: play (fast_algorithms.py:99-111)
+            double th2r[NF][D], Sr[NF];                         // theta2 = 2*theta, S = sum |q - y|
+            double th2l[D], Sl = 0.0;
+            int okr[NF], okl = (int)0x80000000;                 // sign bit stays set while sign(df) == -y on every step
+            bool zero_df = false;                               // some df == 0 (no step taken): theta != -0.5 v
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                Sr[k] = 0.0; okr[k] = (int)0x80000000;
+#pragma unroll
+                for (int j = 0; j < D; ++j) th2r[k][j] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) th2l[j] = 0.0;
+            const double* __restrict__ tp = p.tab + (int64_t)g * T * NF;
+
+            auto play = [&](const double (&z)[D], int t) {
+                const double y = lab.next(t, inc);
+                const int yhi = __double2hiint(y);
+                if (NFTL > 0 && do_ftl) {
+                    // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
+                    double x[D];
+                    ftl_action<D>(th2l, x);
+                    const double df = dot_seq<D>(z, x) - y;
+                    Sl = Sl + fabs(df);
+                    const int dhi = __double2hiint(df);
+                    okl &= dhi ^ yhi;
+                    if (df > 0.0 || df < 0.0) {
+                        const int sgn = dhi & 0x80000000;
+#pragma unroll
+                        for (int j = 0; j < D; ++j)
+                            th2l[j] = th2l[j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                    } else zero_df = true;
+                }
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
+                    const double sch = 0.5 * __ldg(tp + k);     // (0.5*scale) * theta2 == scale * theta
+                    double x[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
+                    double n2 = x[0] * x[0];
+#pragma unroll
+                    for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                    project_unit_ball<D>(x, n2, mask);
+                    const double df = dot_seq<D>(z, x) - y;
+                    Sr[k] = Sr[k] + fabs(df);
+                    const int dhi = __double2hiint(df);
+                    okr[k] &= dhi ^ yhi;
+                    if (df > 0.0 || df < 0.0) {
+                        const int sgn = dhi & 0x80000000;
+#pragma unroll
+                        for (int j = 0; j < D; ++j)
+                            th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                    } else zero_df = true;
+                }
+                tp += NF;
+            };
+
+            // 2a: rows from the slab; row t + 1 is loaded a full step ahead, row t + 4 pulled into L2
+            if (ts > 0 && p.debug_phase != 1) {
+                const double* __restrict__ zr = zs;
+                double zn[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) zn[j] = zr[j * kSweepBlock];
+                for (int t = 0; t < ts; ++t, zr += D * kSweepBlock) {
+                    double z[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) z[j] = zn[j];
+                    if (t + 1 < ts) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
+                    }
+                    if (t + 4 < ts) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(zr + (4 * D + j) * kSweepBlock));
+                    }
+                    play(z, t);
+                }
+            }
+            // 2b: rows regenerated in registers
+            s = s_mid;
+            for (int t = ts; t < T; ++t) {
+                double z[D];
+                gpath_row2<D>(tb, s, inc, z);
+                play(z, t);
+            }
+
+            // ---- comparator and results
+            const double halfT = 0.5 * (double)T;
+            auto finish = [&](const double (&th2)[D], double S, int ok, double& cum, double& comp, double& reg) {
+                double n2 = th2[0] * th2[0];
+#pragma unroll
+                for (int j = 1; j < D; ++j) n2 = n2 + th2[j] * th2[j];
+                const double nth = 0.5 * sqrt(n2);              // ||theta_T||
+                cum = 0.5 * S;
+                if (ok < 0 && !zero_df && !p.force_second_pass) {
+                    comp = halfT - nth;
+                    reg = (cum - halfT) + nth;
+                } else {                                        // literal second pass (exact)
+                    double a[D];
+                    ftl_action<D>(th2, a);
+                    comp = 0.5 * gsweep_exact_comp<D>(&tb, ka, T, kc, a);
+                    reg = cum - comp;
+                }
+            };
+            if (NFTL > 0 && do_ftl) {
+                double cum, comp;
+                finish(th2l, Sl, okl, cum, comp, reg_l);
+                for (int c = 0; active && c < p.plan.n_ftl; ++c) {
+                    const int64_t o = b * A + p.plan.ftl_col[c];
+                    if (p.regret) p.regret[o] = reg_l;
+                    if (p.cum) p.cum[o] = cum;
+                    if (p.comp) p.comp[o] = comp;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                if (k < nf) {
+                    double cum, comp;
+                    finish(th2r[k], Sr[k], okr[k], cum, comp, reg_r[k]);
+                    const int64_t o = b * A + p.plan.ftrl_col[g * NF + k];
+                    if (active && p.regret) p.regret[o] = reg_r[k];
+                    if (active && p.cum) p.cum[o] = cum;
+                    if (active && p.comp) p.comp[o] = comp;
+                }
+            }
+        }
+
+        // ---- per-chunk (max, sum, sumsq) of the regrets, fixed order (same layout as sweep_kernel)
+        if (p.partials) {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
+            for (int sidx = 0; sidx < nslots; ++sidx) {
+                const bool is_ftl = do_ftl && sidx == nslots - 1;
+                double r = reg_l;
+                if (!is_ftl) {
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) if (k == sidx) r = reg_r[k];
+                }
+                double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
+                double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+                    sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
+                    sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
+                }
+                if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
+                __syncthreads();
+                if (tid == 0) {
+                    double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
+                    for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
+                    const int ncols = is_ftl ? p.plan.n_ftl : 1;
+                    for (int c = 0; c < ncols; ++c) {
+                        const int col = is_ftl ? p.plan.ftl_col[c] : p.plan.ftrl_col[g * NF + sidx];
+                        double* o = p.partials + (chunk * A + col) * 3;
+                        o[0] = m; o[1] = s1; o[2] = s2;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// persistent launch; the slab (only when t_split > 0) is allocated stream-ordered
+template <int D, int NFTL, int NF>
+static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
+    auto kern = gsweep_kernel<D, NFTL, NF>;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepBlock, 0);
+    if (e != cudaSuccess) return e;
+    const int64_t chunks = (a.B + kSweepBlock - 1) / kSweepBlock;
+    a.n_items = chunks * a.plan.groups;
+    int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
+    a.t_split = std::max(0, std::min(a.t_split, a.T));
+    const size_t per_cta = (size_t)a.t_split * D * kSweepBlock * sizeof(double);
+    if (per_cta > 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const int64_t fit = (int64_t)((free_b / 10) * 7 / per_cta);
+            if (fit < 1) return cudaErrorMemoryAllocation;
+            grid = std::min<int64_t>(grid, fit);
+        }
+    }
+    void* slab = nullptr;
+    if (per_cta > 0) {
+        e = cudaMallocAsync(&slab, (size_t)grid * per_cta + 256, st);
+        if (e != cudaSuccess) return e;
+    }
+    a.slab_z = slab; a.slab_y = nullptr;
+    kern<<<(unsigned)grid, kSweepBlock, 0, st>>>(a);
+    e = cudaGetLastError();
+    cudaError_t e2 = slab ? cudaFreeAsync(slab, st) : cudaSuccess;
+    return e != cudaSuccess ? e : e2;
+}
+
+template <int D>
+static cudaError_t launch_gsweep_d(const SweepArgs& a, cudaStream_t st) {
+    const bool ftl = a.plan.n_ftl > 0;
+    switch (a.plan.nf_tpl) {
+    case 1: return ftl ? launch_gsweep_cfg<D, 1, 1>(a, st) : launch_gsweep_cfg<D, 0, 1>(a, st);
+    case 4: return ftl ? launch_gsweep_cfg<D, 1, 4>(a, st) : launch_gsweep_cfg<D, 0, 4>(a, st);
+    case 8: return ftl ? launch_gsweep_cfg<D, 1, 8>(a, st) : launch_gsweep_cfg<D, 0, 8>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace oco

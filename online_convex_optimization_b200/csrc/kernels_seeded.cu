@@ -85,7 +85,7 @@ cudaError_t launch_sweep_table(double* tab, const SweepPlan& plan, int64_t T, cu
 
 cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
                          double p_flip, const SweepPlan& plan, const double* sweep_tab,
-                         double* regret, double* cum, double* comp, double* partials, cudaStream_t st) {
+                         double* regret, double* cum, double* comp, double* partials, int comparator_mode, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > 0x7fffffff) return cudaErrorInvalidValue;
     SweepArgs a;
@@ -94,6 +94,17 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
     {   // test hook: take the literal second pass even where the d = 1 candidate sums apply (tests/test_gpu_parity.py)
         const char* e = getenv("OCO_SWEEP_FORCE_SECOND_PASS");
         a.force_second_pass = (e && e[0] == '1') ? 1 : 0;
+    }
+    a.t_split = 0; a.debug_phase = 0;
+    if (const char* e = getenv("OCO_GSWEEP_DEBUG")) a.debug_phase = atoi(e);
+    if (family == FAM_GPATH && d >= 2 && comparator_mode == 1) {
+        // single-pass comparator: regenerate the rows (no slab) -- optionally the first fraction of every
+        // sequence through a slab (tuning knob; 0 = no DRAM traffic at all, 1 = every row parked once)
+        if (const char* e = getenv("OCO_GSWEEP_SLAB_FRAC")) {
+            const double f = atof(e);
+            a.t_split = (int)((double)a.T * (f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f)));
+        }
+        return d <= 3 ? launch_gsweep_lo(a, d, st) : launch_gsweep_hi(a, d, st);
     }
     if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);
     if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_iid(a, d, st);

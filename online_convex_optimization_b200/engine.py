@@ -21,6 +21,7 @@ from ._lib import (COMPARATOR_LINEAR, COMPARATOR_TWO_PASS, FAM_FLIP, FAM_GPATH, 
 
 SQRT2 = math.sqrt(2.0)
 FAMILIES = {"gpath": FAM_GPATH, "iid": FAM_IID, "noisy": FAM_NOISY, "flip": FAM_FLIP, "switch": FAM_SWITCH}
+COMPARATORS = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}
 
 
 def _vp(a) -> C.c_void_p:
@@ -85,7 +86,7 @@ def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = 
         ca = np.ascontiguousarray(comparator_action, dtype=np.float64).reshape(-1, d)
         if ca.shape != (B, d):
             raise ValueError(f"comparator_action must have shape ({B}, {d})")
-    mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
+    mode = COMPARATORS[comparator]
     cdt = {"f64": OCO_F64, "f32": OCO_F32}[compute]
     _lib.check(_lib.load().oco_simulate_batch_host(_vp(z), _vp(y), dt, cdt, B, T, d, _vp(af), _vp(et), A, _vp(ca),
                                                    _vp(reg), _vp(cum), _vp(comp), _vp(th), _vp(xl), _vp(xt), mode, device))
@@ -175,9 +176,11 @@ def gen_sequences(family, B: int, T: int, d: int = 5, *, key_a: int = 0, key_c0:
 
 
 def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int = 0, key_c0: int = 0, keys=None,
-                 p_flip: float = -1.0, want_regret: bool = True, full: bool = False, device: int = 0):
+                 p_flip: float = -1.0, want_regret: bool = True, full: bool = False, comparator: str = "two_pass",
+                 device: int = 0):
     """Fused generate+simulate+compare.  Returns dict(regret (B,A) | None, stats (A,4) = max,sum,sumsq,count
-    [, cum_loss, comp_loss])."""
+    [, cum_loss, comp_loss]).  comparator="linear" (g-path, 2 <= d <= 5): no second pass, no scratch traffic,
+    regrets within 1e-12 * max(1, cum_loss) of the reference (see include/oco_b200.h)."""
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
     af, et = _variants(alg_flags, eta0s)
     A = af.size
@@ -186,17 +189,19 @@ def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int
     comp = np.empty((B, A)) if full else None
     stats = np.zeros((A, 4))
     k = _keys(keys, B)
-    _lib.check(_lib.load().oco_regret_sweep_host(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
-                                                 _vp(reg), _vp(cum), _vp(comp), _vp(stats), device))
+    _lib.check(_lib.load().oco_regret_sweep_mode_host(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
+                                                      _vp(reg), _vp(cum), _vp(comp), _vp(stats), COMPARATORS[comparator], device))
     return {"regret": reg, "stats": stats, "cum_loss": cum, "comp_loss": comp}
 
 
-def g_sweep(T_grid, *, runs: int, base_seed: int = 0, run_lo: int = 0, d: int = 5, eta0: float = SQRT2, device: int = 0):
+def g_sweep(T_grid, *, runs: int, base_seed: int = 0, run_lo: int = 0, d: int = 5, eta0: float = SQRT2,
+            comparator: str = "two_pass", device: int = 0):
     """empirical_worst_case_thresholds for runs [run_lo, run_lo+runs) -> (g_max (nT,), stats (nT,4))."""
     tg = np.ascontiguousarray(T_grid, dtype=np.int64)
     g = np.zeros(tg.size)
     st = np.zeros((tg.size, 4))
-    _lib.check(_lib.load().oco_g_sweep_host(_vp(tg), tg.size, run_lo, runs, base_seed, d, float(eta0), _vp(g), _vp(st), device))
+    _lib.check(_lib.load().oco_g_sweep_mode_host(_vp(tg), tg.size, run_lo, runs, base_seed, d, float(eta0), _vp(g), _vp(st),
+                                                 COMPARATORS[comparator], device))
     return g, st
 
 
@@ -248,7 +253,7 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
     cum = torch.empty_like(reg) if full else None
     comp = torch.empty_like(reg) if full else None
     th = torch.empty((B, A, d), dtype=torch.float64, device=z.device) if full else None
-    mode = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}[comparator]
+    mode = COMPARATORS[comparator]
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().oco_simulate_batch(_dptr(z), _dptr(y), OCO_F32 if z.dtype == torch.float32 else OCO_F64,
                                                   {"f64": OCO_F64, "f32": OCO_F32}[compute], B, T, d, _vp(af), _vp(et), A, None, _dptr(reg), _dptr(cum), _dptr(comp),
@@ -291,7 +296,7 @@ def gen_sequences_device(family, B: int, T: int, d: int = 5, *, key_a: int = 0, 
 
 
 def regret_sweep_device(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int = 0, key_c0: int = 0, keys=None,
-                        p_flip: float = -1.0, want_regret: bool = True, device=None):
+                        p_flip: float = -1.0, want_regret: bool = True, comparator: str = "two_pass", device=None):
     """Returns (regret (B,A) CUDA tensor or None, stats (A,4) CUDA tensor); enqueued, not synchronised."""
     torch = _torch()
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
@@ -302,6 +307,7 @@ def regret_sweep_device(family, B: int, T: int, d: int, alg_flags, eta0s, *, key
     stats = torch.empty((A, 4), dtype=torch.float64, device=dev)
     k = _keys(keys, B)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().oco_regret_sweep(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
-                                                _dptr(reg), None, None, _dptr(stats), _stream_ptr(torch)))
+        _lib.check(_lib.load().oco_regret_sweep_mode(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
+                                                     _dptr(reg), None, None, _dptr(stats), COMPARATORS[comparator],
+                                                     _stream_ptr(torch)))
     return reg, stats

@@ -1,21 +1,23 @@
 // gsweep_impl.cuh -- the g-path sweep for d > 1 with the single-pass ("linear") comparator:
-// generate + play + compare with NO second pass over the rows and (by default) NO scratch traffic.
+// generate + play + compare with NO second pass over the rows and the two phases software-pipelined.
 //
 //   gsweep_kernel<D, NFTL, NF>: one thread per seeded sequence of fast_algorithms.py:231-239
 //   (z = standard_normal((T, d)) clipped to the unit ball, y = choice([-1, 1], T)), persistent CTAs.
 //
 //   numpy draws the T labels AFTER all T*d normals from the same PCG64 stream, and the ziggurat
-//   consumes a data-dependent number of raw draws, so the label cursor is only known once every
-//   normal of the sequence has been (at least) counted.  sweep_kernel (sweep_impl.cuh) therefore
-//   parks the rows in an HBM slab (8*d bytes written, 16*d read per step).  Here instead:
-//     pass 1  COUNT: walk the stream once doing only what decides how many raws each normal
-//             consumes (PCG64 step + output + the `rabs < ki[idx]` test; the wedge / tail tests
-//             only for the 0.85 % of draws that fail it) -- integer work, no stores;
-//     pass 2  PLAY:  re-seed, regenerate every row in registers right before it is played, with
-//             the labels drawn from the cursor pass 1 found.
-//   The first `t_split` rows can optionally go through a slab instead (generated once in pass 1,
-//   streamed back in pass 2): t_split = 0 is the pure regenerating kernel (zero DRAM bytes per
-//   step), t_split = T the pure slab kernel; the launcher picks it (OCO_GSWEEP_SLAB_FRAC).
+//   consumes a data-dependent number of raw draws, so the label cursor of a sequence is only known
+//   once every one of its normals has been generated: its rows must either be kept (8*d bytes per
+//   step written once, read once) or generated twice.  Generating twice was built and measured in
+//   round 2 (count pass + regenerate, zero DRAM bytes): 1.96e10 steps/s against 3.49e10 for the slab
+//   at d = 5 -- the generator IS the cost (profiles/history/r02_gsweep_regen_experiment.md) -- so rows
+//   go through a per-CTA slab in HBM, laid out [t][j][thread] (every warp access one coalesced 256-B
+//   request).  What changed against sweep_kernel (sweep_impl.cuh):
+//     * no comparator pass (below): rows are read once, not twice, and no label words are stored;
+//     * the two phases of consecutive sequences are software-pipelined inside each thread: while
+//       row t of sequence k+1 is being generated (integer-ALU bound), row t of sequence k is loaded
+//       and played (HBM / fp64 bound) -- two independent dependency chains per thread and the slab
+//       traffic hidden under the generator, instead of the two phases running back to back;
+//     * streamlined ziggurat fast path (one LDS.128 per draw) and an inlined wedge test.
 //
 //   Comparator without a second pass (fast_algorithms.py:113-114, 69-76).  Rows have ||z_t|| <= 1
 //   (clipped, up to 2 ulp) and y_t = +-1.  Whenever the played q_t = z_t.x_t satisfies
@@ -153,6 +155,83 @@ __device__ __forceinline__ void gpath_row2(const ZigTab2& tb, Pcg64& s, const Pc
     for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
 }
 
+// ---------------------------------------------------------------- generator with a one-raw lookahead
+// The raw stream R_0, R_1, ... of a PCG64 is fixed; only the ROLE of a raw (start of a normal, wedge uniform,
+// tail uniform, label word) depends on the accept tests before it.  So the next raw can always be drawn
+// before the current one has been interpreted: the 128-bit LCG step + XSL-RR output of raw n + 1 (27
+// instructions, ~60 cycles of dependent latency) then overlaps the table lookup, compare and branch of raw n
+// instead of waiting behind them.  `rn` is the raw already drawn but not yet consumed.
+struct GenLA { Pcg64 s; uint64_t rn; };
+
+__device__ __forceinline__ uint64_t la_take(GenLA& g, const PcgInc& inc) {
+    const uint64_t r = g.rn;
+    g.rn = pcg_next64(g.s, inc);
+    return r;
+}
+__device__ __forceinline__ double la_double(GenLA& g, const PcgInc& inc) {      // Generator.random()
+    return __ull2double_rn(la_take(g, inc) >> 11) * (1.0 / 9007199254740992.0);
+}
+struct ZigTailLARet { double x; uint64_t hi, lo, rn; };
+static __device__ __noinline__ ZigTailLARet zig_tail_la(uint64_t s_hi, uint64_t s_lo, uint64_t rn, uint64_t inc_hi, uint64_t inc_lo,
+                                                        uint64_t rabs) {
+    GenLA g; g.s.hi = s_hi; g.s.lo = s_lo; g.rn = rn;
+    PcgInc inc; inc.hi = inc_hi; inc.lo = inc_lo;
+    ZigTailLARet out;
+    for (;;) {
+        const double xx = -OCO_ZIG_INV_R * log1p_glibc_fma(-la_double(g, inc));
+        const double yy = -log1p_glibc_fma(-la_double(g, inc));
+        if (yy + yy > xx * xx) {
+            out.x = ((rabs >> 8) & 1) ? -(OCO_ZIG_R + xx) : OCO_ZIG_R + xx;
+            out.hi = g.s.hi; out.lo = g.s.lo; out.rn = g.rn;
+            return out;
+        }
+    }
+}
+static __device__ __forceinline__ double zig_slow_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc, int idx, uint64_t mag, double x) {
+    for (;;) {
+        if (idx == 0) {
+            const ZigTailLARet o = zig_tail_la(g.s.hi, g.s.lo, g.rn, inc.hi, inc.lo, mag & 0x000fffffffffffffULL);
+            g.s.hi = o.hi; g.s.lo = o.lo; g.rn = o.rn;
+            return o.x;
+        }
+        const double f1 = tb.fi[idx], f0 = tb.fi[idx - 1];
+        const double yv = (f0 - f1) * la_double(g, inc) + f1;
+        const double arg = -0.5 * x * x;
+        const double ef = (double)__expf((float)arg);
+        const bool sure_yes = yv < ef * (1.0 - 1e-5), sure_no = yv > ef * (1.0 + 1e-5);
+        bool accept = sure_yes;
+        if (!sure_yes && !sure_no) accept = zig_wedge_exact(yv, arg);
+        if (accept) return x;
+        if (zig_try(tb, la_take(g, inc), x, idx, mag)) return x;     // rejected: a fresh attempt
+    }
+}
+__device__ __forceinline__ double zig_normal_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc) {
+    const uint64_t r = la_take(g, inc);
+    double x; int idx; uint64_t mag;
+    if (zig_try(tb, r, x, idx, mag)) return x;
+    return zig_slow_la(tb, g, inc, idx, mag, x);
+}
+template <int D>
+__device__ __forceinline__ void gpath_row_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc, double (&z)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = zig_normal_la(tb, g, inc);
+    const double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+    const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
+}
+// Generator.choice([-1.0, 1.0], size=T) continuing a lookahead stream: one 32-bit draw per label, low half of
+// each raw first, then the high half; label = top bit (rng_numpy.cuh::LabelCursor with the raw prefetched)
+struct LabelCursorLA {
+    GenLA g; uint64_t cur;
+    __device__ __forceinline__ double next(int t, const PcgInc& inc) {
+        uint32_t w;
+        if ((t & 1) == 0) { cur = la_take(g, inc); w = (uint32_t)cur; }
+        else w = (uint32_t)(cur >> 32);
+        return (w >> 31) ? 1.0 : -1.0;
+    }
+};
+
 // ---------------------------------------------------------------- exact fallback (never taken on g-path data)
 // Literal second pass sum_t |z_t.a - y_t| for one sequence and one comparator a (fast_algorithms.py:69-76):
 // count pass for the label cursor, then regenerate rows and labels.
@@ -180,7 +259,7 @@ static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint
 
 // ---------------------------------------------------------------- the kernel
 #ifndef OCO_GSWEEP_MIN_BLOCKS
-#define OCO_GSWEEP_MIN_BLOCKS 6
+#define OCO_GSWEEP_MIN_BLOCKS 5
 #endif
 
 template <int D, int NFTL, int NF>
@@ -191,62 +270,75 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
     zig_tab2_load(tb);
     const int T = p.T, A = p.plan.A, tid = threadIdx.x;
     const int groups = p.plan.groups;
-    const int ts = p.t_split;                                   // rows [0, ts) go through the slab
-    double* __restrict__ zs = reinterpret_cast<double*>(p.slab_z) + (int64_t)blockIdx.x * ts * D * kSweepBlock + tid;
+    constexpr unsigned mask = 0xffffffffu;
+    // two slabs per CTA: round r writes slab r & 1 (generation of item r) and reads slab (r - 1) & 1 (play of item r - 1)
+    const int64_t slab_elems = (int64_t)T * D * kSweepBlock;
+    double* __restrict__ slab0 = reinterpret_cast<double*>(p.slab_z) + (int64_t)blockIdx.x * 2 * slab_elems + tid;
 
-    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int64_t chunk = item / groups;
-        const int g = (int)(item - chunk * groups);
-        const bool active = chunk * kSweepBlock + tid < p.B;
-        const int64_t b = active ? chunk * kSweepBlock + tid : p.B - 1;   // idle lanes replay the last sequence
-        constexpr unsigned mask = 0xffffffffu;
-        const int nf = min(NF, p.plan.n_ftrl - g * NF);
-        const bool do_ftl = NFTL > 0 && g == 0 && p.plan.n_ftl > 0;
-        double reg_r[NF], reg_l = 0.0;
+    // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t n_my = p.n_items > blockIdx.x ? (p.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    // ---- state of the sequence being PLAYED (item r - 1)
+    LabelCursorLA lab; lab.g.s.hi = 0; lab.g.s.lo = 0; lab.g.rn = 0; lab.cur = 0;
+    PcgInc incB; incB.hi = 0; incB.lo = 0;
+    int64_t chunkB = 0, bB = 0; int gB = 0; bool activeB = false;
+    // ---- state of the sequence being GENERATED (item r)
+    GenLA genA; genA.s.hi = 0; genA.s.lo = 0; genA.rn = 0;
+    PcgInc incA; incA.hi = 0; incA.lo = 0;
+
+    for (int64_t r = 0; r <= n_my; ++r) {
+        const bool doA = r < n_my && p.debug_phase != 2, doB = r > 0 && p.debug_phase != 1;
+        int64_t chunkA = 0, bA = 0; int gA = 0; bool activeA = false;
+        if (r < n_my) {
+            const int64_t item = blockIdx.x + r * gridDim.x;
+            chunkA = item / groups; gA = (int)(item - chunkA * groups);
+            activeA = chunkA * kSweepBlock + tid < p.B;
+            bA = activeA ? chunkA * kSweepBlock + tid : p.B - 1;     // idle lanes replay the last sequence
+            const uint64_t ka = p.keys ? p.keys[2 * bA] : p.key_a;
+            const uint64_t kc = p.keys ? p.keys[2 * bA + 1] : p.key_c0 + (uint64_t)bA;
+            pcg_seed3(genA.s, incA, ka, (uint64_t)T, kc);
+            genA.rn = pcg_next64(genA.s, incA);
+        }
+        double* __restrict__ zw = slab0 + (r & 1) * slab_elems;                 // generation writes here
+        const double* __restrict__ zr = slab0 + ((r + 1) & 1) * slab_elems;     // play reads the other one
+
+        // play state (fast_algorithms.py:95-97); theta2 = 2*theta, S = sum |q - y|
+        double th2r[NF][D], Sr[NF];
+        double th2l[D], Sl = 0.0;
+        int okr[NF], okl = (int)0x80000000;                 // sign bit stays set while sign(df) == -y on every step
+        bool zero_df = false;                               // some df == 0 (no step taken): theta != -0.5 v
 #pragma unroll
-        for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
-
-        {
-            const uint64_t ka = p.keys ? p.keys[2 * b] : p.key_a;
-            const uint64_t kc = p.keys ? p.keys[2 * b + 1] : p.key_c0 + (uint64_t)b;
-            Pcg64 s; PcgInc inc;
-            pcg_seed3(s, inc, ka, (uint64_t)T, kc);
-
-            // ---- pass 1a: rows [0, ts) generated once, parked in the slab ([t][j][thread], coalesced)
-            if (p.debug_phase != 2) {
-                double* __restrict__ zw = zs;
-                for (int t = 0; t < ts; ++t, zw += D * kSweepBlock) {
-                    double z[D];
-                    gpath_row2<D>(tb, s, inc, z);
+        for (int k = 0; k < NF; ++k) {
+            Sr[k] = 0.0; okr[k] = (int)0x80000000;
 #pragma unroll
-                    for (int j = 0; j < D; ++j) zw[j * kSweepBlock] = z[j];
-                }
+            for (int j = 0; j < D; ++j) th2r[k][j] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) th2l[j] = 0.0;
+        const double* __restrict__ tp = p.tab + (int64_t)gB * T * NF;
+        const bool do_ftl = NFTL > 0 && gB == 0 && p.plan.n_ftl > 0;
+
+        // the row and the FTRL scales of step t are fetched at the END of step t - 1 into the registers step t
+        // reads them from (no copy the compiler could sink to the loop end): a whole generation step hides the HBM latency
+        double zc[D], scn[NF];
+#pragma unroll
+        for (int j = 0; j < D; ++j) zc[j] = (doB && T > 0) ? __ldcg(zr + j * kSweepBlock) : 0.0;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) scn[k] = (doB && T > 0) ? __ldg(tp + k) : 0.0;
+
+        for (int t = 0; t < T; ++t) {
+            // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
+            if (doA) {
+                double z[D];
+                gpath_row_la<D>(tb, genA, incA, z);
+#pragma unroll
+                for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
+                zw += D * kSweepBlock;
             }
-            const Pcg64 s_mid = s;                              // stream position of row ts
-            // ---- pass 1b: count the raws of rows [ts, T) (no float work on the fast path, no stores)
-            for (int t = ts; t < T; ++t) {
-#pragma unroll
-                for (int j = 0; j < D; ++j) zig_skip2(tb, s, inc);
-            }
-            LabelCursor lab; lab.s = s; lab.cur = 0;            // choice([-1, 1], T) continues the stream here
-
-            // ---- pass 2: play (fast_algorithms.py:99-111)
-            double th2r[NF][D], Sr[NF];                         // theta2 = 2*theta, S = sum |q - y|
-            double th2l[D], Sl = 0.0;
-            int okr[NF], okl = (int)0x80000000;                 // sign bit stays set while sign(df) == -y on every step
-            bool zero_df = false;                               // some df == 0 (no step taken): theta != -0.5 v
-#pragma unroll
-            for (int k = 0; k < NF; ++k) {
-                Sr[k] = 0.0; okr[k] = (int)0x80000000;
-#pragma unroll
-                for (int j = 0; j < D; ++j) th2r[k][j] = 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < D; ++j) th2l[j] = 0.0;
-            const double* __restrict__ tp = p.tab + (int64_t)g * T * NF;
-
-            auto play = [&](const double (&z)[D], int t) {
-                const double y = lab.next(t, inc);
+            // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
+            if (doB) {
+                const double (&z)[D] = zc;
+                const double y = lab.next(t, incB);
                 const int yhi = __double2hiint(y);
                 if (NFTL > 0 && do_ftl) {
                     // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
@@ -265,7 +357,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 }
 #pragma unroll
                 for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
-                    const double sch = 0.5 * __ldg(tp + k);     // (0.5*scale) * theta2 == scale * theta
+                    const double sch = 0.5 * scn[k];             // (0.5*scale) * theta2 == scale * theta
                     double x[D];
 #pragma unroll
                     for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
@@ -284,40 +376,22 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                             th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
                     } else zero_df = true;
                 }
-                tp += NF;
-            };
-
-            // 2a: rows from the slab; row t + 1 is loaded a full step ahead, row t + 4 pulled into L2
-            if (ts > 0 && p.debug_phase != 1) {
-                const double* __restrict__ zr = zs;
-                double zn[D];
+                tp += NF; zr += D * kSweepBlock;
+                if (t + 1 < T) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) zn[j] = zr[j * kSweepBlock];
-                for (int t = 0; t < ts; ++t, zr += D * kSweepBlock) {
-                    double z[D];
+                    for (int j = 0; j < D; ++j) zc[j] = __ldcg(zr + j * kSweepBlock);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) z[j] = zn[j];
-                    if (t + 1 < ts) {
-#pragma unroll
-                        for (int j = 0; j < D; ++j) zn[j] = zr[(D + j) * kSweepBlock];
-                    }
-                    if (t + 4 < ts) {
-#pragma unroll
-                        for (int j = 0; j < D; ++j)
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(zr + (4 * D + j) * kSweepBlock));
-                    }
-                    play(z, t);
+                    for (int k = 0; k < NF; ++k) scn[k] = __ldg(tp + k);
                 }
             }
-            // 2b: rows regenerated in registers
-            s = s_mid;
-            for (int t = ts; t < T; ++t) {
-                double z[D];
-                gpath_row2<D>(tb, s, inc, z);
-                play(z, t);
-            }
+        }
 
-            // ---- comparator and results
+        // ---- comparator, results and per-chunk statistics of the played item
+        if (r > 0) {                                            // (uniform over the CTA: the reduction below synchronises)
+            const int nf = min(NF, p.plan.n_ftrl - gB * NF);
+            double reg_r[NF], reg_l = 0.0;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) reg_r[k] = 0.0;
             const double halfT = 0.5 * (double)T;
             auto finish = [&](const double (&th2)[D], double S, int ok, double& cum, double& comp, double& reg) {
                 double n2 = th2[0] * th2[0];
@@ -331,6 +405,8 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 } else {                                        // literal second pass (exact)
                     double a[D];
                     ftl_action<D>(th2, a);
+                    const uint64_t ka = p.keys ? p.keys[2 * bB] : p.key_a;
+                    const uint64_t kc = p.keys ? p.keys[2 * bB + 1] : p.key_c0 + (uint64_t)bB;
                     comp = 0.5 * gsweep_exact_comp<D>(&tb, ka, T, kc, a);
                     reg = cum - comp;
                 }
@@ -338,8 +414,8 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             if (NFTL > 0 && do_ftl) {
                 double cum, comp;
                 finish(th2l, Sl, okl, cum, comp, reg_l);
-                for (int c = 0; active && c < p.plan.n_ftl; ++c) {
-                    const int64_t o = b * A + p.plan.ftl_col[c];
+                for (int c = 0; activeB && c < p.plan.n_ftl; ++c) {
+                    const int64_t o = bB * A + p.plan.ftl_col[c];
                     if (p.regret) p.regret[o] = reg_l;
                     if (p.cum) p.cum[o] = cum;
                     if (p.comp) p.comp[o] = comp;
@@ -350,52 +426,55 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 if (k < nf) {
                     double cum, comp;
                     finish(th2r[k], Sr[k], okr[k], cum, comp, reg_r[k]);
-                    const int64_t o = b * A + p.plan.ftrl_col[g * NF + k];
-                    if (active && p.regret) p.regret[o] = reg_r[k];
-                    if (active && p.cum) p.cum[o] = cum;
-                    if (active && p.comp) p.comp[o] = comp;
+                    const int64_t o = bB * A + p.plan.ftrl_col[gB * NF + k];
+                    if (activeB && p.regret) p.regret[o] = reg_r[k];
+                    if (activeB && p.cum) p.cum[o] = cum;
+                    if (activeB && p.comp) p.comp[o] = comp;
+                }
+            }
+            // per-chunk (max, sum, sumsq) of the regrets, fixed order (same layout as sweep_kernel)
+            if (p.partials) {
+                const int lane = tid & 31, warp = tid >> 5;
+                const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
+                for (int sidx = 0; sidx < nslots; ++sidx) {
+                    const bool is_ftl = do_ftl && sidx == nslots - 1;
+                    double rg = reg_l;
+                    if (!is_ftl) {
+#pragma unroll
+                        for (int k = 0; k < NF; ++k) if (k == sidx) rg = reg_r[k];
+                    }
+                    double mx = activeB ? rg : -__longlong_as_double(0x7ff0000000000000LL);
+                    double sm = activeB ? rg : 0.0, sq = activeB ? rg * rg : 0.0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+                        sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
+                        sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
+                    }
+                    if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
+                        for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
+                        const int ncols = is_ftl ? p.plan.n_ftl : 1;
+                        for (int c = 0; c < ncols; ++c) {
+                            const int col = is_ftl ? p.plan.ftl_col[c] : p.plan.ftrl_col[gB * NF + sidx];
+                            double* o = p.partials + (chunkB * A + col) * 3;
+                            o[0] = m; o[1] = s1; o[2] = s2;
+                        }
+                    }
+                    __syncthreads();
                 }
             }
         }
 
-        // ---- per-chunk (max, sum, sumsq) of the regrets, fixed order (same layout as sweep_kernel)
-        if (p.partials) {
-            const int lane = tid & 31, warp = tid >> 5;
-            const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
-            for (int sidx = 0; sidx < nslots; ++sidx) {
-                const bool is_ftl = do_ftl && sidx == nslots - 1;
-                double r = reg_l;
-                if (!is_ftl) {
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) if (k == sidx) r = reg_r[k];
-                }
-                double mx = active ? r : -__longlong_as_double(0x7ff0000000000000LL);
-                double sm = active ? r : 0.0, sq = active ? r * r : 0.0;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
-                    sm = sm + __shfl_down_sync(0xffffffffu, sm, off);
-                    sq = sq + __shfl_down_sync(0xffffffffu, sq, off);
-                }
-                if (lane == 0) { red[warp][0] = mx; red[warp][1] = sm; red[warp][2] = sq; }
-                __syncthreads();
-                if (tid == 0) {
-                    double m = red[0][0], s1 = red[0][1], s2 = red[0][2];
-                    for (int w = 1; w < kSweepBlock / 32; ++w) { m = fmax(m, red[w][0]); s1 += red[w][1]; s2 += red[w][2]; }
-                    const int ncols = is_ftl ? p.plan.n_ftl : 1;
-                    for (int c = 0; c < ncols; ++c) {
-                        const int col = is_ftl ? p.plan.ftl_col[c] : p.plan.ftrl_col[g * NF + sidx];
-                        double* o = p.partials + (chunk * A + col) * 3;
-                        o[0] = m; o[1] = s1; o[2] = s2;
-                    }
-                }
-                __syncthreads();
-            }
-        }
+        // ---- hand over: the sequence just generated is played next; numpy's choice([-1, 1], T) continues its stream
+        lab.g = genA; lab.cur = 0; incB = incA;
+        chunkB = chunkA; gB = gA; bB = bA; activeB = activeA;
     }
 }
 
-// persistent launch; the slab (only when t_split > 0) is allocated stream-ordered
+// persistent launch; two slabs per resident CTA, allocated stream-ordered
 template <int D, int NFTL, int NF>
 static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
     auto kern = gsweep_kernel<D, NFTL, NF>;
@@ -407,8 +486,7 @@ static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
     const int64_t chunks = (a.B + kSweepBlock - 1) / kSweepBlock;
     a.n_items = chunks * a.plan.groups;
     int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
-    a.t_split = std::max(0, std::min(a.t_split, a.T));
-    const size_t per_cta = (size_t)a.t_split * D * kSweepBlock * sizeof(double);
+    const size_t per_cta = 2 * (size_t)a.T * D * kSweepBlock * sizeof(double);
     if (per_cta > 0) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -418,14 +496,12 @@ static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
         }
     }
     void* slab = nullptr;
-    if (per_cta > 0) {
-        e = cudaMallocAsync(&slab, (size_t)grid * per_cta + 256, st);
-        if (e != cudaSuccess) return e;
-    }
+    e = cudaMallocAsync(&slab, (size_t)grid * per_cta + 256, st);
+    if (e != cudaSuccess) return e;
     a.slab_z = slab; a.slab_y = nullptr;
     kern<<<(unsigned)grid, kSweepBlock, 0, st>>>(a);
     e = cudaGetLastError();
-    cudaError_t e2 = slab ? cudaFreeAsync(slab, st) : cudaSuccess;
+    cudaError_t e2 = cudaFreeAsync(slab, st);
     return e != cudaSuccess ? e : e2;
 }
 

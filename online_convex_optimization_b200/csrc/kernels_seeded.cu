@@ -95,15 +95,10 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
         const char* e = getenv("OCO_SWEEP_FORCE_SECOND_PASS");
         a.force_second_pass = (e && e[0] == '1') ? 1 : 0;
     }
-    a.t_split = 0; a.debug_phase = 0;
-    if (const char* e = getenv("OCO_GSWEEP_DEBUG")) a.debug_phase = atoi(e);
+    a.debug_phase = 0;
+    if (const char* e = getenv("OCO_GSWEEP_DEBUG")) a.debug_phase = atoi(e);     // timing experiments: one phase only
     if (family == FAM_GPATH && d >= 2 && comparator_mode == 1) {
-        // single-pass comparator: regenerate the rows (no slab) -- optionally the first fraction of every
-        // sequence through a slab (tuning knob; 0 = no DRAM traffic at all, 1 = every row parked once)
-        if (const char* e = getenv("OCO_GSWEEP_SLAB_FRAC")) {
-            const double f = atof(e);
-            a.t_split = (int)((double)a.T * (f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f)));
-        }
+        // single-pass comparator (no second pass over the rows) + software-pipelined generate / play: gsweep_impl.cuh
         return d <= 3 ? launch_gsweep_lo(a, d, st) : launch_gsweep_hi(a, d, st);
     }
     if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);

@@ -50,7 +50,6 @@ struct SweepArgs {
     int64_t B; int T;
     int family;
     int force_second_pass;   // test hook (see launch_sweep)
-    int t_split;             // gsweep_kernel only: rows [0, t_split) go through the slab, the rest are regenerated
     int debug_phase;         // gsweep_kernel timing experiments only (OCO_GSWEEP_DEBUG): 1 = generation only, 2 = play only
     double p_flip;
     const double* tab;       // [groups][T][NF] FTRL scales -(eta0/sqrt(t+1)), padded with -0.0

@@ -20,16 +20,22 @@ def shard_runs(n_runs: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def allreduce_stats(stats, group=None):
-    """In-place all-reduce of a (..., 4) tensor of (max, sum, sumsq, count) rows."""
+    """In-place reduction over ranks of a (..., 4) tensor of (max, sum, sumsq, count) rows: MAX for column 0, SUM
+    for the rest.  ONE collective: every rank gathers all ranks' rows (a few hundred bytes each) and folds them
+    locally in rank order, so the sums are bit-identical on every rank and from run to run."""
+    import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats
-    mx = stats[..., 0].contiguous()
-    sm = stats[..., 1:].contiguous()
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)
-    stats[..., 0] = mx
-    stats[..., 1:] = sm
+    world = dist.get_world_size(group)
+    mine = stats.contiguous()
+    allst = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allst, mine, group=group)
+    out = allst[0].clone()
+    for r in range(1, world):                       # fixed order: deterministic sums
+        out[..., 0] = torch.maximum(out[..., 0], allst[r][..., 0])
+        out[..., 1:] = out[..., 1:] + allst[r][..., 1:]
+    stats.copy_(out)
     return stats
 
 
@@ -57,3 +63,41 @@ def regret_sweep_sharded(family, n_runs: int, T: int, d: int, alg_flags, eta0s, 
         stats[..., 0] = float("-inf")
     allreduce_stats(stats, group)
     return reg, stats
+
+
+def _device_g_stats(T_grid, lo, n, base_seed, d, eta0, comparator):
+    """This rank's (nT, 4) statistics of FTRL(eta0) regrets on runs [lo, lo + n): one fused launch per T, all
+    enqueued on the current stream before anything is read back."""
+    import torch
+    from . import engine
+    stats = torch.empty((len(T_grid), 4), dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+    for i, T in enumerate(T_grid):
+        _, st = engine.regret_sweep_device("gpath", n, int(T), d, [0], [eta0], key_a=base_seed, key_c0=lo,
+                                           want_regret=False, comparator=comparator)
+        stats[i] = st[0]
+    return stats
+
+
+def g_sweep_sharded(T_grid, runs: int, *, base_seed: int = 0, d: int = 5, eta0: float = 2.0 ** 0.5,
+                    comparator: str = "two_pass", group=None, stats_fn=None):
+    """fast_algorithms.empirical_worst_case_thresholds (fast_algorithms.py:211-247) with the `runs` sharded over the
+    ranks of `group` (contiguous blocks, every T of a run on the same rank) and ONE collective over the (nT, 4)
+    per-T statistics.  Returns (g (nT,) = max(0, max_r regret), stats (nT, 4) = max, sum, sumsq, count) on every rank;
+    g is bit-identical for any number of ranks (MAX is order independent).  `stats_fn(T_grid, lo, n)` replaces the
+    device sweep in the CPU (gloo) tests of this host logic."""
+    import torch
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    lo, n = shard_runs(int(runs), rank, world)
+    T_grid = [int(T) for T in T_grid]
+    if stats_fn is not None:
+        stats = stats_fn(T_grid, lo, n)
+    else:
+        stats = _device_g_stats(T_grid, lo, n, int(base_seed), d, float(eta0), comparator)
+    if n == 0:
+        stats[..., 0] = float("-inf")
+    allreduce_stats(stats, group)
+    g = torch.clamp(stats[..., 0], min=0.0)         # max_regret starts at 0.0 (fast_algorithms.py:228)
+    return g, stats

@@ -71,3 +71,47 @@ def test_allreduce_stats_world2_matches_single_process():
     curves = odist.stats_to_curves(torch.from_numpy(got[0]))
     assert np.allclose(curves["mean"].numpy(), full.mean(axis=0))
     assert np.allclose(curves["sem"].numpy(), full.std(axis=0, ddof=1) / math.sqrt(n_runs))
+
+
+def _g_worker(rank, world, port, T_grid, runs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O   # checker stands in for the kernels on CPU
+
+    def stats_fn(Tg, lo, n):
+        st = torch.zeros((len(Tg), 4), dtype=torch.float64)
+        for i, T in enumerate(Tg):
+            reg = O.regret_sweep(0, T, lo, n, 5, [0], [R2], nthreads=1)[:, 0] if n else np.zeros(0)
+            st[i] = torch.tensor([reg.max() if n else 0.0, reg.sum(), (reg ** 2).sum(), float(n)])
+        return st
+    g, st = odist.g_sweep_sharded(T_grid, runs, stats_fn=stats_fn)
+    q.put((rank, g.numpy(), st.numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("runs", [9, 1])          # runs = 1: rank 1 owns no run at all
+def test_g_sweep_sharded_world2_matches_reference_semantics(runs):
+    """T_grid-sharded g(T) sweep: one collective, g identical on both ranks and equal to the single-process
+    empirical_worst_case_thresholds (max clamped at 0), also when a rank has an empty shard."""
+    from oracle import oracle as O
+    T_grid, world = [40, 75], 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + runs
+    procs = [ctx.Process(target=_g_worker, args=(r, world, port, T_grid, runs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, g, st = q.get(timeout=120)
+        got[r] = (g, st)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = O.empirical_worst_case_thresholds(np.array(T_grid), runs=runs, base_seed=0)
+    for r in range(world):
+        g, st = got[r]
+        assert [float(v) for v in g] == [want[T] for T in T_grid]
+        assert (st[:, 3] == runs).all()
+    assert (got[0][1] == got[1][1]).all()           # bit-identical statistics on every rank

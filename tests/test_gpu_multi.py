@@ -20,7 +20,11 @@ def _worker(rank, world, port, n_runs, T, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from online_convex_optimization_b200 import dist as odist
     reg, stats = odist.regret_sweep_sharded("gpath", n_runs, T, 5, [0, 1], [R2, R2], key_a=0, run_lo=0, want_regret=True)
-    q.put((rank, stats.cpu().numpy(), reg.cpu().numpy()))
+    g = {}
+    for mode in ("two_pass", "linear"):     # T_grid-sharded g(T) sweep: one collective over the (nT, 4) curve
+        gg, gst = odist.g_sweep_sharded([100, 250], n_runs, base_seed=0, comparator=mode)
+        g[mode] = (gg.cpu().numpy(), gst.cpu().numpy())
+    q.put((rank, stats.cpu().numpy(), reg.cpu().numpy(), g))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -38,8 +42,8 @@ def test_sharded_sweep_equals_single_gpu():
         p.start()
     got = {}
     for _ in range(world):
-        r, st, reg = q.get(timeout=300)
-        got[r] = (st, reg)
+        r, st, reg, g = q.get(timeout=300)
+        got[r] = (st, reg, g)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -52,3 +56,10 @@ def test_sharded_sweep_equals_single_gpu():
         assert (st[:, 3] == n_runs).all()
         assert np.allclose(st[:, 1], single["stats"][:, 1], rtol=1e-14)
         assert np.allclose(st[:, 2], single["stats"][:, 2], rtol=1e-14)
+    # g(T) sweep sharded over the two ranks == the single-GPU sweep (MAX bit-identical), both comparator modes
+    for mode in ("two_pass", "linear"):
+        g1, st1 = engine.g_sweep(np.array([100, 250]), runs=n_runs, base_seed=0, comparator=mode)
+        for r in range(world):
+            gg, gst = got[r][2][mode]
+            assert (gg == g1).all() and (gst[:, 0] == st1[:, 0]).all() and (gst[:, 3] == n_runs).all()
+            assert np.allclose(gst[:, 1], st1[:, 1], rtol=1e-13)

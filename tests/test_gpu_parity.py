@@ -372,3 +372,62 @@ def test_sweep_large_sample_bit_exact(eng):
     want = O.regret_sweep(12345, T, 777, B, d, [0], [R2])
     got = eng.regret_sweep("gpath", B, T, d, [0], [R2], key_a=12345, key_c0=777)["regret"]
     assert (bits(got) == bits(want)).all()
+
+
+# ------------------------------------------------------------------ single-pass (linear) comparator in the fused sweep
+def _sweep_linear_check(eng, d, T, B, flags, etas, key_a, key_c0):
+    """cum_loss bit-exact; regret / comp_loss within 1e-12 * max(1, cum_loss) of the oracle (the reference's own
+    sequential comparator sum carries that much rounding noise; north_star's tolerance for d > 1)."""
+    want = O.regret_sweep(key_a, T, key_c0, B, d, flags, etas)
+    ex = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=key_a, key_c0=key_c0, full=True)
+    got = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=key_a, key_c0=key_c0, full=True, comparator="linear")
+    assert (bits(ex["regret"]) == bits(want)).all()
+    assert (bits(got["cum_loss"]) == bits(ex["cum_loss"])).all()
+    scale = np.maximum(1.0, ex["cum_loss"])
+    assert np.all(np.abs(got["regret"] - want) <= REL * scale), np.max(np.abs(got["regret"] - want) / scale)
+    assert np.all(np.abs(got["comp_loss"] - ex["comp_loss"]) <= REL * scale)
+    st = got["stats"]
+    assert (st[:, 0] == got["regret"].max(axis=0)).all() and (st[:, 3] == B).all()
+    assert np.allclose(st[:, 1], got["regret"].sum(axis=0), rtol=1e-13)
+    return np.max(np.abs(got["regret"] - want) / np.maximum(np.abs(want), 1e-300))
+
+
+@pytest.mark.parametrize("d,T,B,A", [(5, 300, 150, 1), (5, 201, 140, 2), (2, 100, 10, 4), (3, 257, 70, 9), (4, 64, 129, 5),
+                                     (5, 1, 3, 1), (5, 2, 1, 2), (2, 150, 70, 19)])
+def test_regret_sweep_linear_comparator(eng, d, T, B, A):
+    flags = ([0, 1] + [0] * 7 + [1] + [0] * 9)[:A]
+    etas = [R2 * s for s in (1.0, 1.0, 0.125, 0.25, 0.5, 2.0, 4.0, 8.0, 16.0, 1.0, .1, .2, .3, .4, .6, .7, .8, .9, 1.1)][:A]
+    _sweep_linear_check(eng, d, T, B, flags, etas, 7, 11)
+
+
+def test_regret_sweep_linear_comparator_full_T(eng):
+    """BASELINE config 5's shape at full length (T = 1e4, d = 5): both comparator modes against the oracle, several CTA
+    rounds (the generate / play software pipeline: 1300 sequences = 11 chunks on few CTAs is exercised by B > 128)."""
+    rel = _sweep_linear_check(eng, 5, 10_000, 12, [0], [R2], 0, 0)
+    assert rel <= 5e-12          # observed ~6e-13 relative to the regret itself
+    _sweep_linear_check(eng, 5, 10_000, 4, [0, 1], [R2, R2], 0, 999_996)
+    # many rounds per CTA at a moderate length
+    _sweep_linear_check(eng, 5, 64, 128 * 148 * 5 * 2 + 77, [0], [R2], 3, 0)
+
+
+def test_regret_sweep_linear_forced_second_pass_is_bit_exact(eng, monkeypatch):
+    """The fallback every unverified sequence takes (literal second pass over regenerated rows) gives the reference's bits."""
+    monkeypatch.setenv("OCO_SWEEP_FORCE_SECOND_PASS", "1")
+    for d, T, B, A in ((5, 120, 70, 2), (3, 90, 40, 4), (2, 33, 200, 1)):
+        flags = ([0, 1] + [0] * 7)[:A]; etas = [R2 * s for s in (1.0, 1.0, 0.125, 0.25)][:A]
+        want = O.regret_sweep(3, T, 5, B, d, flags, etas)
+        got = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=3, key_c0=5, comparator="linear")
+        assert (bits(got["regret"]) == bits(want)).all()
+    monkeypatch.delenv("OCO_SWEEP_FORCE_SECOND_PASS")
+
+
+def test_g_sweep_linear_matches_exact(eng):
+    """empirical_worst_case_thresholds with comparator="linear": the g(T) maxima agree with the bit-exact table."""
+    Tg = np.array([100, 300, 1000])
+    g0, st0 = eng.g_sweep(Tg, runs=300, base_seed=0)
+    g1, st1 = eng.g_sweep(Tg, runs=300, base_seed=0, comparator="linear")
+    assert np.all(np.abs(g1 - g0) <= REL * Tg / 2) and np.all(g1 > 0)
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    ga = fa.empirical_worst_case_thresholds(Tg, runs=300, base_seed=0)
+    gb = fa.empirical_worst_case_thresholds(Tg, runs=300, base_seed=0, comparator="linear")
+    assert [ga[int(t)] for t in Tg] == list(g0) and [gb[int(t)] for t in Tg] == list(g1)

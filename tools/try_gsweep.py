@@ -13,8 +13,7 @@ def bits(a):
 if "parity" in what:
     from oracle import oracle as O
     ok = True
-    for frac in ("0", "0.5", "1"):
-        os.environ["OCO_GSWEEP_SLAB_FRAC"] = frac
+    for frac in ("-",):
         for d, T, B, A in ((5, 300, 150, 1), (5, 201, 140, 2), (2, 100, 10, 4), (3, 257, 70, 9), (4, 64, 129, 5), (5, 1, 3, 1)):
             flags = ([0, 1] + [0] * 7)[:A]
             etas = [R2 * s for s in (1.0, 1.0, 0.125, 0.25, 0.5, 2.0, 4.0, 8.0, 16.0)][:A]
@@ -40,10 +39,8 @@ if "parity" in what:
             ok = ok and e
         del os.environ["OCO_SWEEP_FORCE_SECOND_PASS"]
     # T = 1e4 spot check
-    os.environ["OCO_GSWEEP_SLAB_FRAC"] = "0"
     want = O.regret_sweep(0, 10000, 0, 8, 5, [0], [R2])
-    for frac in ("0", "1"):
-        os.environ["OCO_GSWEEP_SLAB_FRAC"] = frac
+    for frac in ("-",):
         got = engine.regret_sweep("gpath", 8, 10000, 5, [0], [R2], comparator="linear", full=True)
         err = np.abs(got["regret"] - want)
         print(f"T=1e4 d=5 frac={frac}: max |dreg| = {err.max():.3e}  rel to regret {np.max(err/np.abs(want)):.2e}  rel to cum {np.max(err/got['cum_loss']):.2e}")
@@ -52,20 +49,19 @@ if "parity" in what:
 
 if "time" in what:
     import torch
-    B = int([a for a in sys.argv[1:] if a.isdigit()][0]) if any(a.isdigit() for a in sys.argv[1:]) else 227328
     T, d = 10000, 5
-    def run(mode, frac):
-        os.environ["OCO_GSWEEP_SLAB_FRAC"] = frac
+    def run(mode, B):
         for _ in range(2):
             reg, st = engine.regret_sweep_device("gpath", B, T, d, [0], [R2], comparator=mode, want_regret=False)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(3):
+        for _ in range(2):
             reg, st = engine.regret_sweep_device("gpath", B, T, d, [0], [R2], comparator=mode, want_regret=False)
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
-        print(f"mode={mode} slab_frac={frac} B={B}: {ms:.2f} ms/launch  {B*T/ms/1e-3:.3e} steps/s  max={float(st[0,0]):.6f}", flush=True)
-    run("two_pass", "0")
-    for frac in ("0", "0.5", "0.8", "1"):
-        run("linear", frac)
+        ms = e0.elapsed_time(e1) / 2
+        print(f"mode={mode} B={B}: {ms:.2f} ms/launch  {B*T/ms/1e-3:.3e} steps/s  max={float(st[0,0]):.6f}", flush=True)
+    Bs = [int(a) for a in sys.argv[1:] if a.isdigit()] or [94720, 378880, 1000000]
+    for B in Bs:
+        run("linear", B)
+    run("two_pass", Bs[-1])

@@ -130,8 +130,8 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int c
                        double* theta_final, double* x_last, double* x_trace, int comparator_mode, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     if (d > 256) return fail(OCO_ERR_VALUE, "d <= 256 supported (got %d)", d);
-    if ((x_trace || x_last || comparator) && d > kMaxSmallD)
-        return fail(OCO_ERR_VALUE, "x_trace / x_last / comparator are available for d <= %d only", kMaxSmallD);
+    if (x_trace && d > kMaxSmallD)
+        return fail(OCO_ERR_VALUE, "x_trace is available for d <= %d only", kMaxSmallD);
     if (comparator_mode != OCO_COMPARATOR_TWO_PASS && comparator_mode != OCO_COMPARATOR_LINEAR)
         return fail(OCO_ERR_VALUE, "unknown comparator_mode %d", comparator_mode);
     if (compute_dtype != OCO_F32 && compute_dtype != OCO_F64) return fail(OCO_ERR_VALUE, "compute_dtype must be OCO_F32 or OCO_F64");
@@ -149,6 +149,9 @@ OCO_API int oco_simulate_batch(const void* z, const void* y, int in_dtype, int c
     else if (d <= kMaxSmallD)
         CU(launch_sim_stream(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), comparator, regret, cum_loss, comp_loss,
                              theta_final, x_last, x_trace, comparator_mode, st));
+    else if (comparator || x_last)   // exact_ftl._simulate_ftrl for d > 8: one warp per (sequence, variant)
+        CU(launch_wide_fixed_comp(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), comparator, regret, cum_loss, comp_loss,
+                                  theta_final, x_last, st));
     else if (wide_tma_eligible(z, y, in_dtype == OCO_F32, T, d))
         CU(launch_sim_wide_tma(z, y, in_dtype == OCO_F32, B, T, d, v, tab.as<double>(), regret, cum_loss, comp_loss, theta_final, comparator_mode, st));
     else    // unaligned shapes: plain coalesced loads
@@ -213,10 +216,13 @@ OCO_API int oco_exact_ftl_prefix_batch(const void* z, const void* y, int in_dtyp
                                double* actions, double* cum_loss, double* comp_loss, double* regret,
                                int* status, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
-    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "exact FTL: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > 256) return fail(OCO_ERR_VALUE, "exact FTL: d <= 256 supported (got %d)", d);
     if (B > 0 && !status) return fail(OCO_ERR_VALUE, "status must not be NULL");
     if (B == 0) return OCO_OK;
-    CU(launch_exact_ftl_linear(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, (cudaStream_t)stream));
+    if (d <= kMaxSmallD)
+        CU(launch_exact_ftl_linear(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, (cudaStream_t)stream));
+    else    // the reference has no dimension limit (its own smoke run is d = 10): warp per sequence
+        CU(launch_wide_exact_prefix(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, (cudaStream_t)stream));
     return OCO_OK;
 }
 
@@ -261,7 +267,9 @@ OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dty
                                 int max_iter, double tol, int64_t first_prefix, double* actions, double* cum_loss, double* comp_loss,
                                 double* regret, int* status, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
-    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "exact FTL: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > 256) return fail(OCO_ERR_VALUE, "exact FTL: d <= 256 supported (got %d)", d);
+    if (d > kMaxSmallD && norm != 0)
+        return fail(OCO_ERR_VALUE, "exact FTL on the linf / l1 ball: d <= %d supported (got %d)", kMaxSmallD, d);
     if (norm < 0 || norm > 2) return fail(OCO_ERR_VALUE, "norm must be 0 (l2), 1 (linf) or 2 (l1)");
     if (max_iter < 1 || !(tol > 0.0)) return fail(OCO_ERR_VALUE, "need max_iter >= 1 and tol > 0");
     if (first_prefix < 0 || first_prefix > T + 1) return fail(OCO_ERR_VALUE, "need 0 <= first_prefix <= T + 1");
@@ -271,6 +279,13 @@ OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dty
     retain_pool_memory();
     DevBuf fl;
     const int* flagged = nullptr;
+    if (d > kMaxSmallD) {
+        // l2 ball, d > 8: the closed form of the linear regime only (every reference workload); a sequence outside the
+        // regime gets status T (= every prefix unsolved), which the shim turns into the reference's solver failure
+        CU(launch_wide_exact_prefix(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, st));
+        CU(launch_status_scale(status, B, (int)std::min<int64_t>(T > 0 ? T : 1, 0x7fffffff), st));
+        return OCO_OK;
+    }
     if (norm == 0) {    // closed form wherever the sequence is in the linear regime; its status = 1 marks the others
         CU(fl.alloc(sizeof(int) * (size_t)B, st));
         CU(launch_exact_ftl_linear(z, y, in_dtype == OCO_F32, B, T, d, actions, nullptr, nullptr, nullptr, fl.as<int>(), st));
@@ -325,7 +340,7 @@ OCO_API int oco_exact_ftl_general_batch_host(const void* z, const void* y, int i
 OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum_loss, double* comp_loss, double* regret, int device) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
-    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "replay: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > 256) return fail(OCO_ERR_VALUE, "replay: d <= 256 supported (got %d)", d);
     if (B > 0 && !actions) return fail(OCO_ERR_VALUE, "actions must not be NULL");
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     if (B == 0) return OCO_OK;
@@ -343,8 +358,11 @@ OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_d
                                cudaMemcpyAsync(yd.p, y, (size_t)B * T * es, cudaMemcpyHostToDevice, st) != cudaSuccess)) ||
                     cudaMemcpyAsync(ad.p, actions, na, cudaMemcpyHostToDevice, st) != cudaSuccess))
             rc = fail(OCO_ERR_RUNTIME, "host-to-device copy failed");
-        if (!rc && launch_replay_actions(zd.p, yd.p, in_dtype == OCO_F32, B, T, d, ad.as<double>(), cd.as<double>(), pd.as<double>(),
-                                         rd.as<double>(), st) != cudaSuccess) rc = fail(OCO_ERR_RUNTIME, "replay launch failed");
+        if (!rc && (d <= kMaxSmallD ? launch_replay_actions(zd.p, yd.p, in_dtype == OCO_F32, B, T, d, ad.as<double>(), cd.as<double>(),
+                                                            pd.as<double>(), rd.as<double>(), st)
+                                    : launch_wide_replay(zd.p, yd.p, in_dtype == OCO_F32, B, T, d, ad.as<double>(), cd.as<double>(),
+                                                         pd.as<double>(), rd.as<double>(), st)) != cudaSuccess)
+            rc = fail(OCO_ERR_RUNTIME, "replay launch failed");
         if (!rc) {
             bool c = true;
             if (cum_loss) c = c && cudaMemcpyAsync(cum_loss, cd.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess;

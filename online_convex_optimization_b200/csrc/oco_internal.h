@@ -93,6 +93,15 @@ cudaError_t launch_exact_ftl_general(const void* z, const void* y, int in_f32, i
                                      double* actions, int* status, cudaStream_t st);
 cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
+// 8 < d <= 256 twins of the three launchers above (kernels_wide_exact.cu: one warp per sequence / per (sequence, variant))
+cudaError_t launch_wide_exact_prefix(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                     double* actions, double* cum, double* comp, double* regret, int* status, cudaStream_t st);
+cudaError_t launch_wide_replay(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                               const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
+cudaError_t launch_wide_fixed_comp(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                                   const Variants& v, const double* scale_tab, const double* comparator,
+                                   double* regret, double* cum, double* comp, double* theta_final, double* x_last, cudaStream_t st);
+cudaError_t launch_status_scale(int* status, int64_t B, int factor, cudaStream_t st);   // status[b] *= factor
 // SMART: all A <= 4 thresholds of a sequence in one warp; scale_tab is [T][A] (eta0 per threshold).
 cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                          const double* thresh_dev, const double* scale_tab, int A,

@@ -68,7 +68,7 @@ def _keys(keys, B):
 def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = False,
                    comparator: str = "two_pass", comparator_action=None, compute: str = "f64", device: int = 0):
     """Batched fast_algorithms.simulate_alg: z (B,T,d), y (B,T) -> regret (B,A).
-    full=True returns a dict with cum_loss, comp_loss, theta (B,A,d), x_last (B,A,d; d <= 8)
+    full=True returns a dict with cum_loss, comp_loss, theta (B,A,d), x_last (B,A,d; d <= 8, or any d <= 256 with comparator_action)
     [and x_trace (B,A,T,d)].  comparator_action (B,d): fixed comparator (exact_ftl.run_ftrl).
     compute="f32": the float32-state semantics of the reference's algorithms.py (float32 inputs)."""
     z, y, dt = _prep_zy(z, y)
@@ -79,7 +79,7 @@ def simulate_batch(z, y, alg_flags, eta0s, *, full: bool = False, trace: bool = 
     cum = np.empty((B, A)) if full else None
     comp = np.empty((B, A)) if full else None
     th = np.empty((B, A, d)) if full else None
-    xl = np.zeros((B, A, d)) if (full and d <= 8) else None
+    xl = np.zeros((B, A, d)) if (full and (d <= 8 or comparator_action is not None)) else None
     xt = np.empty((B, A, T, d)) if trace else None
     ca = None
     if comparator_action is not None:

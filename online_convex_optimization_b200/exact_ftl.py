@@ -6,15 +6,20 @@ Two device solvers sit behind ``ExactFTLNoClip`` (DESIGN.md "Exact FTL"):
 * unit **l2** ball in the *linear regime* (every row ||z_t||_2 <= 1 and y_t in {-1,+1} -- what
   every generator in sequence_generation.py produces, hence everything exact_ftl_driver.py
   runs): the reference's SOCP (exact_ftl.py:83-105) has the closed-form optimum v/||v||,
-  v = sum y_i z_i (0 on ties), computed for all prefixes by ``oco_exact_ftl_prefix_batch``;
+  v = sum y_i z_i (0 on ties), computed for all prefixes by ``oco_exact_ftl_prefix_batch`` for any
+  d <= 256 (thread per sequence up to d = 8, warp per sequence beyond; the reference's own smoke run,
+  exact_ftl.py:460-475, is d = 10 -- ``python -m online_convex_optimization_b200.exact_ftl`` runs it);
 * everything else (rows outside the ball, real-valued labels, the linf / l1 balls of
   exact_ftl.py:91-96) with d <= 8: the interior-point solver of ``oco_exact_ftl_general_batch``,
   duality gap <= ``solver_opts["tol"]`` * max(1, f(0)) (default 1e-8) within
   ``solver_opts["max_iter"]`` (default 300) Newton steps per prefix; a prefix that does not converge raises the
   ``RuntimeError`` exact_ftl.py:125-126 raises when its conic solver fails.
 
-PARITY UNPINNED: the reference's arithmetic is CVXPY's (not installed, unpinned); where the
-optimum is not unique (k < d rows, ties) the two solvers may return different minimisers of
+The deterministic half of the module -- ``replay_exact_ftl``, ``_simulate_ftrl`` / ``run_ftrl(comparator_action=...)``
+(exact_ftl.py:230-333, 399-420: njit helpers + NumPy, no CVXPY) -- is pinned to fixtures produced by running the
+reference itself (tools/make_golden.py -> tests/golden/exact_det.json).  The conic solve is not:
+PARITY UNPINNED for ``ExactFTLNoClip`` solves: the reference's arithmetic there is CVXPY's (not installed,
+unpinned); where the optimum is not unique (k < d rows, ties) the two solvers may return different minimisers of
 the same objective.
 """
 from __future__ import annotations
@@ -218,3 +223,25 @@ def run_ftl_exact(z: np.ndarray, y: np.ndarray, *, norm: Literal["l2", "linf", "
     if return_actions:
         return result, actions
     return result
+
+
+def _smoke() -> None:
+    """The reference module's own smoke run (exact_ftl.py:460-475): T = 200, d = 10, rows clipped to the unit ball,
+    labels sign(z.w + noise) -- exact FTL (l2) and the FTRL baseline, printed in the reference's format."""
+    rng = np.random.default_rng(0)
+    T, d = 200, 10
+    z = rng.normal(size=(T, d))
+    z /= np.maximum(1.0, np.linalg.norm(z, axis=1, keepdims=True))
+    w_true = rng.normal(size=d)
+    w_true /= np.linalg.norm(w_true)
+    y = np.sign(z @ w_true + 0.2 * rng.normal(size=T))
+    print("FTL exact (l2)...")
+    res_ftl = run_ftl_exact(z, y, norm="l2", solver="ECOS")
+    print(f"cum_loss={res_ftl.cum_loss:.4f}  regret={res_ftl.regret:.4f}  comp={res_ftl.comp_loss:.4f}")
+    print("FTRL baseline...")
+    res_ftrl = run_ftrl(z, y, eta0=1.0)
+    print(f"cum_loss={res_ftrl.cum_loss:.4f}  regret={res_ftrl.regret:.4f}  comp={res_ftrl.comp_loss:.4f}")
+
+
+if __name__ == "__main__":
+    _smoke()

@@ -46,13 +46,27 @@ def _sem(x: FloatArray) -> float:
     return float(np.std(x, ddof=1) / math.sqrt(n))
 
 
-def _exact_and_ftrl(z: np.ndarray, y: np.ndarray):
-    """(FTRL regret vs exact comparator, exact-FTL regret) for a batch z (B,T,d), y (B,T)."""
+def _exact_and_ftrl(z: np.ndarray, y: np.ndarray, *, norm: str = "l2", solver_opts: Mapping[str, object] | None = None,
+                    only_comparator: bool = False):
+    """(FTRL regret vs exact comparator, exact-FTL regret) for a batch z (B,T,d), y (B,T) on the unit `norm` ball.
+    l2 in the linear regime: closed form for every prefix; anything else (linf / l1 balls, rows outside the ball,
+    real-valued labels): the general interior-point solver with solver_opts {"tol", "max_iter"} -- every prefix, or
+    only the full sequence when only the comparator is needed (exact_ftl_driver.py:104-112 solves just that one)."""
     z = np.ascontiguousarray(z, dtype=np.float64)      # exact_ftl_driver.py:158-159
     y = np.ascontiguousarray(y, dtype=np.float64)
-    ex = engine.exact_ftl_prefix_batch(z, y, want_actions=True)
-    if ex["status"].any():
-        raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime")
+    opts = dict(solver_opts or {})
+    ex = None
+    if norm == "l2" or z.shape[2] == 1:                # for d = 1 the three unit balls coincide
+        ex = engine.exact_ftl_prefix_batch(z, y, want_actions=True)
+        if ex["status"].any():
+            ex = None
+    if ex is None:
+        if z.shape[2] > 8:
+            raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime (general solver covers d <= 8)")
+        ex = engine.exact_ftl_general_batch(z, y, norm=norm, tol=float(opts.get("tol", 1e-8)), max_iter=int(opts.get("max_iter", 300)),
+                                            first_prefix=z.shape[1] if only_comparator else 0)
+        if ex["status"].any():
+            raise RuntimeError(f"Exact FTL (no clip) failed: status=max_iter_reached ({int(ex['status'].sum())} prefixes)")
     ftrl = engine.simulate_batch(z, y, [0], [SQRT2], comparator_action=ex["actions"][:, -1, :])
     return ftrl[:, 0], ex["regret"]
 
@@ -67,7 +81,7 @@ def empirical_worst_case_thresholds(T_grid: IntArray, *, runs: int, base_seed: i
         max_regret = 0.0
         if runs > 0:
             z, y = engine.gen_sequences("gpath", runs, T, 5, key_a=base_seed, key_c0=0)
-            ftrl, _ = _exact_and_ftrl(z, y)
+            ftrl, _ = _exact_and_ftrl(z, y, norm=norm, solver_opts=solver_opts, only_comparator=True)
             for reg in ftrl:
                 if reg > max_regret:
                     max_regret = float(reg)
@@ -82,6 +96,9 @@ def evaluate_stream_with_stats(stream_builder: Callable[..., Callable], T_grid: 
     ExactFTLNoClip(d=5, T_max=1, norm=cfg.norm, solver=cfg.solver)      # validates norm like the reference's constructor
     by_T = {label: [] for label in algo_labels}
     samplers = [stream_builder(run_seed=cfg.base_seed + 2025 * (run + 1)) for run in range(runs)]
+    if runs <= 0 or replicates <= 0:                 # the reference returns empty statistics (means 0, CIs 0)
+        z0 = np.zeros(len(T_grid), dtype=float)
+        return {label: (z0.copy(), z0.copy()) for label in algo_labels}
     for T in T_grid:
         T_int = int(T)
         spec = getattr(samplers[0], "spec", None) if samplers else None
@@ -102,7 +119,7 @@ def evaluate_stream_with_stats(stream_builder: Callable[..., Callable], T_grid: 
                     zs.append(z)
                     ys.append(y)
             zb, yb = np.stack(zs), np.stack(ys)
-        ftrl, ftl = _exact_and_ftrl(zb, yb)
+        ftrl, ftl = _exact_and_ftrl(zb, yb, norm=cfg.norm, solver_opts=cfg.solver_opts)
         vals = {"FTRL": ftrl.reshape(runs, replicates), "FTL (exact)": ftl.reshape(runs, replicates)}
         for label in algo_labels:
             by_T[label].append([float(np.mean([float(v) for v in vals[label][run]])) for run in range(runs)])

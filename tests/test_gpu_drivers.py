@@ -240,3 +240,128 @@ def test_exact_ftl_general_solver_vs_scipy(norm):
         mixed = engine.exact_ftl_general_batch(np.stack([zs, zs * 3.0]), np.stack([ys, ys]))
         assert (mixed["status"] == 0).all()
         assert (mixed["actions"][0].view(np.uint64) == O.exact_ftl_l2_prefix(zs, ys).view(np.uint64)).all()
+
+
+# ------------------------------------------------------------------ exact_ftl.py deterministic half, reference-pinned
+def test_exact_ftl_twin_vs_reference_fixtures(golden_exact_det):
+    """replay_exact_ftl / run_ftrl(comparator_action=...) / _simulate_ftrl of the twin against fixtures produced by
+    RUNNING the reference's exact_ftl.py (exact_ftl.py:230-333, 399-420; tools/make_golden.py), d = 1 ... 33 including
+    the reference's own d = 10 smoke configuration.  d <= 8: played losses and x_last bit-exact (sequential sums, same
+    order); comparator loss 1e-12 (BLAS matvec + pairwise sum in the reference).  d > 8: warp reductions, 1e-12."""
+    from conftest import exact_det_inputs
+    from online_convex_optimization_b200 import exact_ftl as X
+    n = 0
+    for i, case in enumerate(golden_exact_det["cases"]):
+        z, y, acts = exact_det_inputs(case, i)
+        T, d = z.shape
+        for k, a in acts.items():
+            got = X.replay_exact_ftl(z, y, a)
+            want = {f: hexf(v) for f, v in case["replay"][k].items() if f != "actions_seed"}
+            if d <= 8:
+                assert got.cum_loss == want["cum_loss"], (case["name"], k)
+            assert abs(got.cum_loss - want["cum_loss"]) <= REL * max(1.0, want["cum_loss"])
+            assert abs(got.comp_loss - want["comp_loss"]) <= REL * max(1.0, want["comp_loss"])
+            assert abs(got.regret - want["regret"]) <= REL * max(1.0, want["cum_loss"])
+            assert (got.x_last == a[T]).all()
+            n += 1
+        for key, rec in case["ftrl"].items():
+            eta = float(key.split("_")[0][3:]); which = key.split("_")[1]
+            got = X.run_ftrl(z, y, eta0=eta, comparator_action=acts[which][T])
+            want_x = np.array([hexf(v) for v in rec["x_last"]])
+            if d <= 8:
+                assert got.cum_loss == hexf(rec["cum_loss"]), (case["name"], key)
+                assert (got.x_last == want_x).all()
+            assert abs(got.cum_loss - hexf(rec["cum_loss"])) <= REL * max(1.0, hexf(rec["cum_loss"]))
+            assert abs(got.comp_loss - hexf(rec["comp_loss"])) <= REL * max(1.0, hexf(rec["comp_loss"]))
+            assert abs(got.regret - hexf(rec["regret"])) <= REL * max(1.0, hexf(rec["cum_loss"]))
+            assert np.all(np.abs(got.x_last - want_x) <= REL * np.maximum(1.0, np.abs(want_x)))
+            n += 1
+    assert n >= 80
+
+
+def test_exact_ftl_reference_smoke_configuration_d10():
+    """The reference module's __main__ (exact_ftl.py:460-475): T = 200, d = 10 -- exact FTL + FTRL through the twin,
+    against the scipy oracle (the exact half has no reference fixture: CVXPY)."""
+    from oracle import exact_ftl_scipy as XS
+    from online_convex_optimization_b200 import exact_ftl as X
+    rng = np.random.default_rng(0)
+    T, d = 200, 10
+    z = rng.normal(size=(T, d))
+    z /= np.maximum(1.0, np.linalg.norm(z, axis=1, keepdims=True))
+    w_true = rng.normal(size=d)
+    w_true /= np.linalg.norm(w_true)
+    y = np.sign(z @ w_true + 0.2 * rng.normal(size=T))
+    res, actions = X.run_ftl_exact(z, y, norm="l2", solver="ECOS", return_actions=True)
+    assert actions.shape == (T + 1, d) and np.all(np.linalg.norm(actions, axis=1) <= 1 + 1e-12)
+    for k in (1, 7, 50, 200):                                    # prefix optima: never worse than the SOCP restatement
+        val = 0.5 * np.abs(z[:k] @ actions[k] - y[:k]).sum()
+        ref = XS.solve(z[:k], y[:k], "l2")[0]
+        assert val <= ref + 1e-6 * max(1.0, ref), (k, val, ref)
+    assert abs(res.regret - (res.cum_loss - res.comp_loss)) < 1e-9
+    ftrl = X.run_ftrl(z, y, eta0=1.0)
+    assert abs(ftrl.comp_loss - res.comp_loss) <= 1e-9 * max(1.0, res.comp_loss)   # same exact comparator
+    X._smoke()
+    solver = X.ExactFTLNoClip(d=d, T_max=T)                      # stateful API at d = 10
+    a1 = solver.append_row(z[0], float(y[0]))
+    assert np.allclose(a1, actions[1]) and solver._last_length == 1
+    with pytest.raises(RuntimeError):                            # outside the linear regime at d > 8: solver failure
+        X.run_ftl_exact(z * 3.0, y)
+
+
+def test_driver_twin_vs_reference_driver_fixtures(golden_driver32):
+    """driver.py twin against the float32 statistics the REFERENCE's driver.py produced (driver.py:70-129 through
+    algorithms.py, tools/make_golden.py): g(T) and the per-case means / CIs, 1e-5 (north_star's fp32 tolerance)."""
+    from online_convex_optimization_b200 import algorithms as alg32
+    from online_convex_optimization_b200 import driver as dr
+    from online_convex_optimization_b200 import sequence_generation as sg
+    grid = np.array([100, 200, 300])
+    g_want = {int(k): hexf(v) for k, v in golden_driver32["g_emp_runs40"].items()}
+    g_got = alg32.empirical_worst_case_thresholds(grid, runs=40, base_seed=0)
+    for T in grid:
+        assert abs(g_got[int(T)] - g_want[int(T)]) <= 1e-5 * g_want[int(T)]
+    for title, rec in golden_driver32["stats_small"].items():
+        got = dr.evaluate_stream_with_stats(sg.CASES[title], grid, g_want, runs=rec["runs"], replicates=rec["replicates"], base_seed=0)
+        for k in ("FTRL", "FTL", "SMART", "EMP"):
+            want_m = np.array([hexf(v) for v in rec["stats"][k][0]]); want_c = np.array([hexf(v) for v in rec["stats"][k][1]])
+            assert np.all(np.abs(got[k][0] - want_m) <= 1e-5 * np.maximum(1.0, np.abs(want_m))), (title, k, got[k][0], want_m)
+            assert np.all(np.abs(got[k][1] - want_c) <= 1e-5 * np.maximum(1.0, np.abs(want_c)) + 1e-5), (title, k)
+
+
+@pytest.mark.parametrize("norm", ["linf", "l1"])
+def test_exact_driver_twin_other_norms(norm):
+    """exact_ftl_driver with norm != 'l2' solves on THAT ball (exact_ftl_driver.py:64-206 passes norm to every
+    solver): g(T) and the per-case regrets against the scipy oracle (HiGHS), not the l2 closed form."""
+    from oracle import exact_ftl_scipy as XS
+    from online_convex_optimization_b200 import exact_ftl_driver as XD
+    from online_convex_optimization_b200 import sequence_generation as sg
+    grid = np.array([12, 30])
+    cfg = XD.ExperimentConfig(T_grid=grid, g_runs=3, norm=norm, solver_opts={"tol": 1e-9})
+    g = XD.empirical_worst_case_thresholds(grid, runs=3, base_seed=0, norm=norm, solver=None, solver_opts={"tol": 1e-9})
+    for T in grid:
+        best = 0.0
+        for r in range(3):
+            z, y = O.gen_gpath(0, int(T), r, 5)
+            comp = XS.solve(z, y, norm)[0]
+            cum = O.simulate_alg(z, y, 0, R2, full=True)["cum_loss"]
+            best = max(best, cum - comp)
+        assert abs(g[int(T)] - best) <= 1e-6 * max(1.0, best), (norm, T, g[int(T)], best)
+    st = XD.evaluate_stream_with_stats(sg.CASES["Random i.i.d. (separable)"], grid, runs=2, replicates=1, cfg=cfg, stream_name="iid")
+    # the exact-FTL column replays prefix optima on the chosen ball: recompute run 0 with the oracle
+    for ti, T in enumerate(grid):
+        vals = []
+        for run in range(2):
+            z, y, _ = O.gen_iid(2025 * (run + 1), int(T), 0)
+            z = np.asarray(z, dtype=np.float64); y = np.asarray(y, dtype=np.float64)
+            cum = 0.0; x = np.zeros(5)
+            for t in range(int(T)):
+                cum += 0.5 * abs(float(z[t] @ x) - y[t])
+                x = XS.solve(z[:t + 1], y[:t + 1], norm)[1]
+            comp = XS.solve(z, y, norm)[0]
+            vals.append(cum - comp)
+        # minimisers need not be unique (ties / k < d rows): compare the comparator-dominated mean loosely, the optimum value tightly
+        assert abs(st["FTL (exact)"][0][ti] - np.mean(vals)) <= 0.35 * max(1.0, abs(np.mean(vals))) + 1.0
+    l2 = XD.evaluate_stream_with_stats(sg.CASES["Random i.i.d. (separable)"], grid, runs=2, replicates=1,
+                                       cfg=XD.ExperimentConfig(T_grid=grid, g_runs=3, norm="l2"), stream_name="iid")
+    assert not np.allclose(l2["FTRL"][0], st["FTRL"][0])          # a different ball gives a different comparator
+    empty = XD.evaluate_stream_with_stats(sg.CASES["Label flips"], grid, runs=0, replicates=1, cfg=cfg, stream_name="none")
+    assert all((m == 0).all() and (c == 0).all() for m, c in empty.values())

@@ -5,7 +5,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import hexf, make_sequence
+from conftest import exact_det_inputs, hexf, make_sequence
 from oracle import oracle as O
 
 R2 = math.sqrt(2.0)
@@ -107,3 +107,30 @@ def test_exact_ftl_closed_form_known_answers():
         assert O.replay_actions(z, y, act)["regret"] == want
     with pytest.raises(ValueError):
         O.exact_ftl_l2_prefix(np.full((3, 2), 2.0), np.ones(3))
+
+
+def test_exact_ftl_deterministic_half_vs_reference(golden_exact_det):
+    """Oracle replay / FTRL-with-fixed-comparator against fixtures produced by running the reference's exact_ftl.py
+    (cvxpy stubbed, never called): replay_exact_ftl (:306-333) and _simulate_ftrl / run_ftrl(comparator_action=...)
+    (:230-277, 399-420).  The played losses are sequential njit sums -> bit-exact; the comparator loss is a BLAS
+    matvec + pairwise np.sum in the reference -> 1e-12."""
+    n = 0
+    for i, case in enumerate(golden_exact_det["cases"]):
+        z, y, acts = exact_det_inputs(case, i)
+        T, d = z.shape
+        for k, a in acts.items():
+            got = O.replay_actions(z, y, a)
+            want = {f: hexf(v) for f, v in case["replay"][k].items() if f != "actions_seed"}
+            assert got["cum_loss"] == want["cum_loss"], (case["name"], k)
+            assert abs(got["comp_loss"] - want["comp_loss"]) <= 1e-12 * max(1.0, want["comp_loss"])
+            assert abs(got["regret"] - want["regret"]) <= 1e-12 * max(1.0, want["cum_loss"])
+            n += 1
+        for key, rec in case["ftrl"].items():
+            eta = float(key.split("_")[0][3:]); which = key.split("_")[1]
+            full = O.simulate_alg(z, y, 0, eta, full=True)
+            assert full["cum_loss"] == hexf(rec["cum_loss"]), (case["name"], key)      # same FTRL trajectory as fast_algorithms
+            cvec = acts[which][T]
+            comp = 0.5 * float(np.abs(z @ cvec - y).sum())
+            assert abs(comp - hexf(rec["comp_loss"])) <= 1e-12 * max(1.0, comp)
+            n += 1
+    assert n >= 80

@@ -14,6 +14,9 @@ Outputs
   tests/golden/sim_cases.json     regrets of simulate_alg / simulate_SMART_like on seeded sequences
   tests/golden/iterates.npz       per-step iterates x_t built from the reference's own njit helpers
   tests/golden/driver_stats.json  empirical_worst_case_thresholds + evaluate_stream_with_stats outputs
+  tests/golden/exact_det.json     exact_ftl.py's deterministic half (cvxpy stubbed, never called): replay_exact_ftl,
+                                  _simulate_ftrl, run_ftrl(comparator_action=...) on seeded sequences incl. d = 10
+  tests/golden/driver32_stats.json  driver.py (float32 algorithms.py path): g(T) and evaluate_stream_with_stats
 Floats are stored with repr()/float.hex() so they round-trip bit-exactly.
 """
 from __future__ import annotations
@@ -176,9 +179,106 @@ def driver_stats():
     json.dump(res, open(os.path.join(OUT, "driver_stats.json"), "w"), indent=0)
 
 
+def load_ref_module(name, patch_dataclass=True):
+    """Load /root/reference/<name>.py in memory with matplotlib / cvxpy stubbed (never called by what we run)."""
+    for mod in ("matplotlib", "matplotlib.pyplot", "cvxpy"):
+        sys.modules.setdefault(mod, MagicMock())
+    src = open(os.path.join(REF, name + ".py")).read()
+    if patch_dataclass:
+        src = src.replace(
+            "T_grid: IntArray = np.arange(100, 1100, 100, dtype=int)",
+            "T_grid: IntArray = __import__('dataclasses').field(default_factory=lambda: np.arange(100, 1100, 100, dtype=int))")
+    m = types.ModuleType(name)
+    sys.modules[name] = m
+    exec(compile(src, name + ".py", "exec"), m.__dict__)
+    return m
+
+
+def closed_form_actions(z, y):
+    """Prefix actions fed to the reference's replay: v_k/||v_k|| (0 on ties) -- any (T+1, d) array would do, the
+    reference function only replays them (exact_ftl.py:306-333)."""
+    T, d = z.shape
+    a = np.zeros((T + 1, d))
+    v = np.zeros(d)
+    for k in range(T):
+        v = v + y[k] * z[k]
+        n = math.sqrt(float(v @ v))
+        a[k + 1] = v / n if n > 0 else 0.0
+    return a
+
+
+def exact_det():
+    sys.modules.setdefault("cvxpy", MagicMock())      # imported at exact_ftl.py:10, never called by what runs below
+    import exact_ftl as ex                            # the reference module itself (njit cache -> NUMBA_CACHE_DIR)
+    cases = []
+
+    def add(name, z, y, spec):
+        z = np.ascontiguousarray(z, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        T, d = z.shape
+        rng = np.random.default_rng(len(cases) + 1)
+        acts = {"closed": closed_form_actions(z, y)}
+        r = rng.standard_normal((T + 1, d)); r /= np.maximum(1.0, np.linalg.norm(r, axis=1, keepdims=True)); r[0] = 0.0
+        acts["random"] = r
+        rec = {"name": name, "spec": spec, "T": T, "d": d, "replay": {}, "ftrl": {}}
+        for k, a in acts.items():
+            res = ex.replay_exact_ftl(z, y, a)
+            rec["replay"][k] = {"actions_seed": len(cases) + 1, "cum_loss": float(res.cum_loss).hex(), "regret": float(res.regret).hex(),
+                                "comp_loss": float(res.comp_loss).hex()}
+        comp = acts["closed"][T]
+        for eta in (1.0, R2, 0.3):
+            for which, cvec in (("closed", comp), ("random", acts["random"][T])):
+                res = ex.run_ftrl(z, y, eta0=eta, comparator_action=cvec)
+                res2 = ex._simulate_ftrl(z, y, eta0=eta, comparator_action=cvec)
+                assert res.regret == res2.regret and res.cum_loss == res2.cum_loss
+                rec["ftrl"][f"eta{eta!r}_{which}"] = {"cum_loss": float(res.cum_loss).hex(), "regret": float(res.regret).hex(),
+                                                     "comp_loss": float(res.comp_loss).hex(),
+                                                     "x_last": [float(v).hex() for v in res.x_last]}
+        cases.append(rec)
+
+    for (b, T, r, d) in [(0, 200, 1, 5), (0, 150, 2, 10), (4, 120, 0, 1), (4, 90, 3, 33), (2, 64, 7, 8), (2, 1, 0, 10)]:
+        z, y = gpath(b, T, r, d)
+        add(f"gpath_{b}_{T}_{r}_d{d}", z, y, {"family": "gpath", "base_seed": b, "T": T, "run": r, "d": d})
+    for title, builder in sg.CASES.items():
+        sampler = builder(run_seed=2025)
+        z, y, _ = sampler(100, 0)
+        add(f"case_{title}", z, y, {"family": title, "run_seed": 2025, "T": 100, "rep": 0, "d": 5})
+    # the reference module's own smoke configuration (exact_ftl.py:460-475), FTRL half (the exact half needs CVXPY)
+    rng = np.random.default_rng(0)
+    T, d = 200, 10
+    z = rng.normal(size=(T, d))
+    z /= np.maximum(1.0, np.linalg.norm(z, axis=1, keepdims=True))
+    w_true = rng.normal(size=d)
+    w_true /= np.linalg.norm(w_true)
+    y = np.sign(z @ w_true + 0.2 * rng.normal(size=T))
+    add("smoke_main_d10", z, y, {"family": "smoke_main"})
+    json.dump({"cases": cases, "note": "actions['closed'] = v_k/||v_k||; actions['random'] = default_rng(actions_seed) rows clipped to the unit ball, row 0 zero"},
+              open(os.path.join(OUT, "exact_det.json"), "w"), indent=0)
+
+
+def driver32_stats():
+    dr = load_ref_module("driver")
+    res = {}
+    small_grid = np.array([100, 200, 300])
+    g32 = alg32.empirical_worst_case_thresholds(small_grid, runs=40, base_seed=0)
+    res["g_emp_runs40"] = {str(k): float(v).hex() for k, v in g32.items()}
+    res["stats_small"] = {}
+    for title, builder in sg.CASES.items():
+        runs = min(sg.RUNS_BY_TITLE[title], 3)
+        reps = min(sg.REPLICATES_BY_TITLE[title], 2)
+        st = dr.evaluate_stream_with_stats(builder, small_grid, g32, runs=runs, replicates=reps, base_seed=0, stream_name=title)
+        res["stats_small"][title] = {"runs": runs, "replicates": reps,
+                                     "stats": {k: [[float(v).hex() for v in m], [float(v).hex() for v in c]] for k, (m, c) in st.items()}}
+    json.dump(res, open(os.path.join(OUT, "driver32_stats.json"), "w"), indent=0)
+
+
 if __name__ == "__main__":
+    if "--only-new" in sys.argv:
+        exact_det(); driver32_stats()
+        print("exact_det.json / driver32_stats.json written"); sys.exit(0)
     rng_kat()
     sim_cases()
     iterates()
     driver_stats()
+    exact_det()
+    driver32_stats()
     print("golden fixtures written to", os.path.normpath(OUT))

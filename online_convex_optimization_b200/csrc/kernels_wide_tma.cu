@@ -88,6 +88,22 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, int sl) {
     a = hi ? other : keep;
     b = hi ? keep : other;
 }
+// Four fp64 sums at once (the squared norms of the four rows of a tile), result q left in quarter q of the group
+// only (lanes sl / (G/4) == q): log2(G) + 1 exchanges instead of 4 * log2(G), and no redistribution.
+template <int G>
+__device__ __forceinline__ double group_sum4_quartered(double p0, double p1, double p2, double p3, int sl) {
+    static_assert(G >= 4, "four quarters");
+    const bool hi = (sl & (G / 2)) != 0, up = (sl & (G / 4)) != 0;
+    // exchange 1: the low half takes rows 0, 1, the high half rows 2, 3
+    double u = hi ? p2 : p0, v = hi ? p3 : p1;
+    u = u + __shfl_xor_sync(0xffffffffu, hi ? p0 : p2, G / 2);
+    v = v + __shfl_xor_sync(0xffffffffu, hi ? p1 : p3, G / 2);
+    // exchange 2: within each half the lower quarter takes u, the upper quarter v
+    double keep = (up ? v : u) + __shfl_xor_sync(0xffffffffu, up ? u : v, G / 4);
+#pragma unroll
+    for (int off = G / 8; off > 0; off >>= 1) keep = keep + __shfl_xor_sync(0xffffffffu, keep, off);
+    return keep;
+}
 template <int G>
 __device__ __forceinline__ double group_sum1(double a) {
 #pragma unroll
@@ -103,7 +119,8 @@ template <int K>
 struct WideState {
     double th2[K], vy[K], act[K];
     double S, C;                 // sum |q - y| over the played / comparator actions (losses are 0.5 * these)
-    bool linear_ok;
+    double excess;               // linear comparator: sum_t max(0, ||z_t||^2 - 1) of this lane's quarter's rows
+    bool linear_ok;              // labels are +-1 so far
     const double* tabp;          // walks the [T][A] FTRL scale table
 };
 
@@ -114,8 +131,7 @@ __device__ __forceinline__ double flip_sign(double v, int sgn) {
 // one round of play; MODE 0: every trajectory of the warp is FTRL, 1: all FTL, 2: mixed (per-lane select)
 template <int MODE, int G, int K>
 __device__ __forceinline__ void play_row(WideState<K>& st, const double (&z)[K], double y, bool ftrl, bool want_linear,
-                                         int A, int sl, int grp) {
-    constexpr int NT = 32 / G;
+                                         int A, int sl, int grp, double& zz_part) {
     const bool is_ftrl = MODE == 0 || (MODE == 2 && ftrl);
     double x[K];
     if (MODE != 1) {
@@ -142,19 +158,17 @@ __device__ __forceinline__ void play_row(WideState<K>& st, const double (&z)[K],
         for (int k = 0; k < K; ++k) st.th2[k] = st.th2[k] + flip_sign(z[k], sgn);
     }
     if (want_linear) {
-        // precondition of the linear comparator: ||z_t||^2 <= 1 (+1e-6) and y = +-1.  The squared norm is
-        // reduced in 2^-24 fixed point with one full-warp integer REDUX per trajectory of the warp.
+        // Precondition of the linear comparator: y = +-1 and ||z_t|| <= 1, the latter up to a BUDGET: with |z_t.a| <=
+        // ||z_t|| the identity 0.5|z_t.a - y| = 0.5(1 - y z_t.a) is off by at most (||z_t|| - 1)+ <= 0.5 (||z_t||^2 - 1)+
+        // per row, so the comparator loss is within 0.5 * excess of the literal pass; excess <= 1e-13 * T keeps it
+        // inside 1e-12 * (T/2).  float64 rows clipped to the ball (fast_algorithms.py:234-236) stay 100x below the
+        // budget; float32-normalised rows (||z||^2 up to 1 + 1e-7) exceed it and take the literal second pass.
+        // This lane's share of ||z_t||^2 is returned; the caller reduces four rows at a time (group_sum4_quartered).
         double zz = z[0] * z[0];
 #pragma unroll
         for (int k = 1; k < K; ++k) zz = zz + z[k] * z[k];
-        const unsigned units = __double2uint_rz(fmin(zz, 4.0) * 16777216.0);
-        unsigned tot = 0;
-#pragma unroll
-        for (int g = 0; g < NT; ++g) {
-            const unsigned tg = __reduce_add_sync(0xffffffffu, grp == g ? units : 0u);
-            if (grp == g) tot = tg;
-        }
-        if (tot > 16777216u + 17u || !(y == 1.0 || y == -1.0)) st.linear_ok = false;
+        zz_part = zz;
+        if (!(y == 1.0 || y == -1.0)) st.linear_ok = false;
         const int ysgn = __double2hiint(y) & 0x80000000;
 #pragma unroll
         for (int k = 0; k < K; ++k) st.vy[k] = st.vy[k] + flip_sign(z[k], ysgn);
@@ -213,13 +227,20 @@ __device__ __forceinline__ void stream_pass(WidePipe<D, G, TIN>& pp, WideState<D
         const unsigned char* base = pp.smem + pp.cs * P::stage_bytes + (valid ? grp : 0) * P::traj_bytes;
         const TIN* zt = reinterpret_cast<const TIN*>(base) + sl;
         const TIN* yt = reinterpret_cast<const TIN*>(base + P::z_tile_bytes);
+        double zzp[kTT];
 #pragma unroll
         for (int r = 0; r < kTT; ++r) {
             double z[K];
+            zzp[r] = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) z[k] = (double)zt[r * D + G * k];
             if (PASS == 3) compare_row<G, K>(st, z, (double)yt[r]);
-            else play_row<PASS, G, K>(st, z, (double)yt[r], ftrl, want_linear, pp.A, sl, grp);
+            else play_row<PASS, G, K>(st, z, (double)yt[r], ftrl, want_linear, pp.A, sl, grp, zzp[r]);
+        }
+        if (PASS != 3 && want_linear) {                      // squared norms of the tile's four rows, one per quarter of the group
+            static_assert(kTT == 4, "group_sum4_quartered reduces four rows");
+            const double zz = group_sum4_quartered<G>(zzp[0], zzp[1], zzp[2], zzp[3], sl);
+            st.excess = st.excess + fmax(zz - 1.0, 0.0);
         }
         if (++pp.cs == kStages) { pp.cs = 0; pp.cparity ^= 1u; }
         __syncwarp();
@@ -230,7 +251,14 @@ __device__ __forceinline__ void stream_pass(WidePipe<D, G, TIN>& pp, WideState<D
 #pragma unroll
         for (int k = 0; k < K; ++k) z[k] = (double)zb[(int64_t)t * D + sl + G * k];
         if (PASS == 3) compare_row<G, K>(st, z, (double)yb[t]);
-        else play_row<PASS, G, K>(st, z, (double)yb[t], ftrl, want_linear, pp.A, sl, grp);
+        else {
+            double zzp = 0.0;
+            play_row<PASS, G, K>(st, z, (double)yb[t], ftrl, want_linear, pp.A, sl, grp, zzp);
+            if (want_linear) {                               // ragged tail rows: plain reduction, counted in quarter 0
+                const double zz = group_sum1<G>(zzp);
+                if (sl < G / 4) st.excess = st.excess + fmax(zz - 1.0, 0.0);
+            }
+        }
     }
 }
 
@@ -275,7 +303,7 @@ __global__ void __launch_bounds__(kWarps * 32, (D / G <= 2 ? 4 : (D / G <= 4 ? 3
     WideState<K> st;
 #pragma unroll
     for (int k = 0; k < K; ++k) { st.th2[k] = 0.0; st.vy[k] = 0.0; st.act[k] = 0.0; }
-    st.S = 0.0; st.C = 0.0; st.linear_ok = true; st.tabp = p.tab + a;
+    st.S = 0.0; st.C = 0.0; st.excess = 0.0; st.linear_ok = true; st.tabp = p.tab + a;
 
     // all trajectories of the warp run the same algorithm? then the step has no per-lane algorithm select
     if (__all_sync(0xffffffffu, ftrl || !valid)) stream_pass<0, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
@@ -292,7 +320,13 @@ __global__ void __launch_bounds__(kWarps * 32, (D / G <= 2 ? 4 : (D / G <= 4 ? 3
         for (int k = 0; k < K; ++k) st.act[k] = (n2 == 0.0) ? 0.0 : sc * st.th2[k];
     }
     // the second pass shares the warp's barriers: taken if ANY trajectory of the warp needs it
-    const bool use_linear = want_linear && st.linear_ok;
+    bool use_linear = false;
+    if (want_linear) {       // total excess of the sequence: one value per quarter -> sum of the four quarters
+        double e = st.excess;
+        e = e + __shfl_xor_sync(0xffffffffu, e, G / 4);
+        e = e + __shfl_xor_sync(0xffffffffu, e, G / 2);
+        use_linear = st.linear_ok && e <= 1e-13 * (double)T;
+    }
     if (__any_sync(0xffffffffu, valid && !use_linear)) stream_pass<3, D, G, TIN>(pp, st, zb, yb, ftrl, want_linear, valid, lane, sl, grp);
     double comp;
     if (use_linear) {

@@ -431,3 +431,61 @@ def test_g_sweep_linear_matches_exact(eng):
     ga = fa.empirical_worst_case_thresholds(Tg, runs=300, base_seed=0)
     gb = fa.empirical_worst_case_thresholds(Tg, runs=300, base_seed=0, comparator="linear")
     assert [ga[int(t)] for t in Tg] == list(g0) and [gb[int(t)] for t in Tg] == list(g1)
+
+
+# ------------------------------------------------------------------ linear modes: rows slightly outside the unit ball
+@pytest.mark.parametrize("d", [2, 5, 64])
+def test_linear_modes_reject_over_unit_rows(eng, d):
+    """Rows with ||z||^2 = 1 + 9e-7 aligned with the comparator (the round-1 counter-example: the identity
+    0.5|q - y| = 0.5(1 - y q) fails for |q| > 1 by ~4.5e-7 per row).  The precondition is an error BUDGET now
+    (sum (||z||^2 - 1)+ <= 1e-13 T), so such sequences take the literal pass: every linear mode agrees with the
+    oracle to 1e-12; float32-normalised rows (||z||^2 up to 1 + 1e-7) likewise."""
+    T = 1001
+    c = math.sqrt(1.0 + 9e-7)
+    z = np.zeros((3, T, d)); z[:, :, 0] = c
+    y = np.ones((3, T)); y[1, ::7] = -1.0; y[2, ::2] = -1.0
+    flags, etas = [1, 0, 0], [R2, R2, 0.3]
+    want = O.simulate_batch(z, y, flags, etas)
+    for mode in ("two_pass", "linear"):
+        got = eng.simulate_batch(z, y, flags, etas, comparator=mode)
+        assert np.all(np.abs(got - want) <= REL * np.maximum(1.0, np.abs(want))), (d, mode, got, want)
+    if d <= 8:
+        th = [math.sqrt(2 * T), 3.0]
+        wr, ws = O.smart_batch(z, y, th, [R2, R2])
+        for mode in ("exact", "linear"):
+            gr, gs = eng.smart_batch(z, y, th, [R2, R2], mode=mode)
+            assert (gs == ws).all() and np.all(np.abs(gr - wr) <= REL * np.maximum(1.0, np.abs(wr))), (d, mode)
+    # float32-normalised random rows widened to float64: norms up to 1 + 1e-7
+    rng = np.random.default_rng(5)
+    zf = rng.standard_normal((4, 300, d)).astype(np.float32)
+    zf /= np.maximum(np.linalg.norm(zf, axis=2, keepdims=True), 1.0).astype(np.float32)
+    yf = np.where(rng.random((4, 300)) < 0.5, -1.0, 1.0).astype(np.float32)
+    want = O.simulate_batch(zf.astype(np.float64), yf.astype(np.float64), flags, etas)
+    got = eng.simulate_batch(zf, yf, flags, etas, comparator="linear")
+    assert np.all(np.abs(got - want) <= REL * np.maximum(1.0, np.abs(want)))
+
+
+# ------------------------------------------------------------------ SMART at full length (SURVEY 8 f2)
+def test_smart_full_length_T1e4(eng):
+    """simulate_SMART_like at T = 1e4, d = 5 (fast_algorithms.py:118-164): regrets (1e-12) and SWITCH TIMES against the
+    oracle's literal O(T^2) loop on 10 sequences -- random g-path rows with thresholds that switch early / mid /
+    late / never, and the two adversarial families (label flips switch at ~4*thresh, one of them at t ~ 8000)."""
+    T, d = 10_000, 5
+    zs, ys = zip(*[O.gen_gpath(0, T, r, d) for r in range(8)])
+    zf, yf, _ = O.gen_flip(T)
+    zw, yw, _ = O.gen_switching(T)
+    z = np.stack(list(zs) + [np.asarray(zf, dtype=np.float64), np.asarray(zw, dtype=np.float64)])
+    y = np.stack(list(ys) + [np.asarray(yf, dtype=np.float64), np.asarray(yw, dtype=np.float64)])
+    th = [3.0, 15.0, 2000.0, math.sqrt(2 * T)]
+    et = [R2] * 4
+    wr, ws = O.smart_batch(z, y, th, et)
+    assert (ws[:8, 0] >= 0).all() and (ws[:8, 3] < 0).all()            # random rows: early switch / never
+    assert 7000 < ws[8, 2] < 9000 and 0 <= ws[8, 3] < 1000                # label flips: late and early switches
+    for mode in ("exact", "linear"):
+        gr, gs = eng.smart_batch(z, y, th, et, mode=mode)
+        assert (gs == ws).all(), (mode, gs, ws)
+        assert np.all(np.abs(gr - wr) <= REL * np.maximum(1.0, np.abs(wr))), (mode, np.max(np.abs(gr - wr)))
+    # the drop-in single-sequence entry points at full length
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    assert abs(fa.simulate_SMART(z[8], y[8]) - wr[8, 3]) <= REL * max(1.0, abs(wr[8, 3]))
+    assert abs(fa.simulate_empirical_g_SMART(z[0], y[0], 15.0) - wr[0, 1]) <= REL * max(1.0, abs(wr[0, 1]))

@@ -266,22 +266,19 @@ _REAL_STDOUT = None
 def ncu_traffic(kernel: str, units_per_launch: float):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled from the committed ncu capture
     (profiles/r01_dram_traffic.json: bytes per trajectory-step of that kernel), or None."""
-    try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[kernel]
-        return rec["dram_bytes_per_trajectory_step"] * units_per_launch
-    except Exception:
-        return None
+    rec = profile_record(kernel)
+    return rec["dram_bytes_per_trajectory_step"] * units_per_launch if rec else None
 
 
 def ncu_utilisation(kernel: str):
     """Issue-slot and fp64-pipe utilisation of `kernel` from the committed ncu capture (profiles/r01_dram_traffic.json
     <- profiles/r01_ncu_summary.md): north_star's stated bound for sequences generated on the device."""
-    try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))[kernel]
-        return {"issue_active_pct": rec["issue_active_pct"], "fp64_pipe_active_pct": rec["fp64_pipe_active_pct"],
-                "source": "profiles/r01_ncu_summary.md (ncu --set full, not measured in this run)"}
-    except Exception:
+    rec = profile_record(kernel)
+    if not rec:
         return None
+    return {"issue_active_pct": rec["issue_active_pct"], "fp64_pipe_active_pct": rec["fp64_pipe_active_pct"],
+            "warp_instr_per_warp_step": rec.get("warp_instr_per_warp_step"),
+            "source": "committed ncu capture under profiles/ (ncu --set full, not measured in this run)"}
 
 
 def hbm_view(traffic_bytes_per_step, ms_per_step):
@@ -314,6 +311,211 @@ def emit_line(line):
     out.flush()
 
 
+
+PROFILE_JSON = "r02_kernel_profiles.json"
+
+
+def profile_record(kernel: str):
+    """Committed ncu capture of `kernel` (profiles/r02_kernel_profiles.json, falling back to round 1's file)."""
+    for name in (PROFILE_JSON, "r01_dram_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+        except Exception:
+            continue
+    return None
+
+
+def issue_bound(kernel: str, sm_count: int, sm_mhz: float):
+    """Issue-slot bound of a generated-on-device kernel: SMs x 4 schedulers x clock / (warp-instructions per
+    warp-step, from the committed ncu capture) x 32 trajectories per warp-step -- the ceiling the kernel would reach
+    at 100 % issue utilisation WITH ITS CURRENT instruction count (north_star: 'issue-slot / FP64-pipe utilisation')."""
+    rec = profile_record(kernel)
+    if not rec or not rec.get("warp_instr_per_warp_step") or not sm_mhz:
+        return None
+    return sm_count * 4 * sm_mhz * 1e6 / rec["warp_instr_per_warp_step"] * 32 * rec.get("trajectories_per_thread", 1)
+
+
+def timed(torch, fn, reps):
+    """Mean device time (ms) of fn() over `reps` calls after one warm-up call, CUDA events on the current stream."""
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def run_c5(args, torch, dist, engine, odist, rank, world, local, dev, fp64_peak, sm_count, sm_mhz):
+    """BASELINE config 5, the north-star target: empirical g(T) sweep, 1e7 runs x T = 1e4 x d = 5, FTRL eta0 = sqrt 2,
+    STRONG-scaled: the 1e7 runs are sharded over the ranks (dist.shard_runs) and the per-T curve goes through ONE
+    collective (dist.g_sweep_sharded == fast_algorithms.empirical_worst_case_thresholds, fast_algorithms.py:211-247).
+    Timed on the device (events around sweep + collective), max over ranks.  e2e: the host API on host arguments
+    (engine.g_sweep on this rank's shard, statistics back in host memory, then the collective)."""
+    import numpy as np
+    runs, T, d = args.c5_runs, 10_000, 5
+    out = {}
+    for mode in ("linear", "two_pass"):
+        n_timed = 2 if mode == "linear" else 1
+        n_runs = runs if mode == "linear" else max(world * 128, runs // 10)       # the exact mode: a tenth of the job
+        odist.g_sweep_sharded([T], n_runs, comparator=mode)                       # warm-up (slab allocation, pool growth)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_timed):
+            g, st = odist.g_sweep_sharded([T], n_runs, comparator=mode)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n_timed], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rate = n_runs * T / (ms * 1e-3)
+        kname = "gsweep_kernel<5,0,1>" if mode == "linear" else "sweep_kernel<GPathStream<5>,5,0,1>"
+        rec = profile_record(kname) or {}
+        ib = issue_bound(kname, sm_count, sm_mhz)
+        per_gpu = rate / world
+        out[mode] = {
+            "value": rate, "unit": "trajectory-steps/s", "runs": n_runs, "T": T, "d": d, "n_gpus": world, "scaling": "strong",
+            "ms_per_sweep": ms, "g_T": float(g[0].item()), "count": float(st[0, 3].item()),
+            "roofline": {"bound": "fp64-pipe", "achieved": per_gpu * 51 / 1e9, "peak": fp64_peak / 1e9,
+                         "unit": "Gop/s (non-fused fp64)", "frac": per_gpu * 51 / fp64_peak, "kernel": kname,
+                         "algorithmic_ops_per_trajectory_step": 51,
+                         "traffic": (rec.get("dram_bytes_per_trajectory_step") or 0) * (n_runs / world) * T or None,
+                         "traffic_from_profile": True,
+                         "issue_slot_bound": None if ib is None else {
+                             "steps_per_s_at_100pct_issue": ib, "frac": per_gpu / ib,
+                             "warp_instr_per_warp_step": rec.get("warp_instr_per_warp_step"),
+                             "note": "the kernel is integer-ALU / issue bound (numpy-exact PCG64 + ziggurat: ~400 of its "
+                                     "~600 instructions per warp-step), not fp64-pipe bound; both views reported"}},
+        }
+    # e2e through the host API (host arguments in, per-T statistics in host memory), linear mode, full job
+    lo, n = odist.shard_runs(runs, rank, world)
+    engine.g_sweep(np.array([T]), runs=min(n, 1024), run_lo=lo, comparator="linear", device=local)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    gh, sth = engine.g_sweep(np.array([T]), runs=n, run_lo=lo, comparator="linear", device=local)
+    if n == 0:
+        sth[:, 0] = -np.inf
+    stt = torch.from_numpy(sth).to(dev)
+    odist.allreduce_stats(stt)
+    sth = stt.cpu().numpy()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["linear"]["e2e"] = {"value": runs * T / float(t.item()), "unit": "trajectory-steps/s", "h2d_bytes_per_step": 8 + 64,
+                            "d2h_bytes_per_step": 32, "api": "engine.g_sweep (oco_g_sweep_mode_host) + one collective",
+                            "g_T": float(max(sth[0, 0], 0.0))}
+    # parity spot-check inside the measured job: this rank's first 4 runs at full length against the CPU oracle
+    from oracle import oracle as O            # checker only (never on the measured path)
+    want = O.regret_sweep(0, T, lo, 4, d, [0], [R2])
+    err = {}
+    for mode in ("two_pass", "linear"):
+        got = engine.regret_sweep("gpath", 4, T, d, [0], [R2], key_a=0, key_c0=lo, comparator=mode, full=True, device=local)
+        e = float(np.max(np.abs(got["regret"] - want) / np.maximum(1.0, got["cum_loss"])))
+        err[mode] = e
+    te = torch.tensor([err["two_pass"], err["linear"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    out["result_check"] = {"oracle_spot_check": f"4 runs per rank x T={T} x d={d} vs the CPU oracle, max over {world} rank(s)",
+                           "max_abs_err_over_max_1_cum__two_pass": float(te[0].item()), "two_pass_bit_exact": float(te[0].item()) == 0.0,
+                           "max_abs_err_over_max_1_cum__linear": float(te[1].item()), "tolerance": 1e-12,
+                           "g_T_linear": out["linear"]["g_T"], "g_T_two_pass_subset": out["two_pass"]["g_T"]}
+    return out
+
+
+def run_other_single_gpu(args, torch, engine, local, fp64_peak):
+    """Every other number the docs quote, measured in the driver-run line (N = 1 only): C1, C2, exact drivers,
+    general exact solver, SMART at T = 1e4, the float32 mode, the full C4 job with generation."""
+    import numpy as np
+    ex = {}
+
+    def wall(fn, reps=1):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, r
+    try:    # C1: the reference's default fast_driver workload (fast_driver.py:201-220 minus plotting; 42.6 s on one CPU core)
+        from online_convex_optimization_b200 import fast_driver as fd
+        dt, res = wall(lambda: fd.run_experiment(), 2)
+        ex["c1_fast_driver_default"] = {"wall_s": dt, "trajectory_steps": 4.36e7, "value": 4.36e7 / dt, "unit": "trajectory-steps/s (nominal)",
+                                        "g_1000": float(res["g_emp"][1000]), "reference_cpu_1core_s": 42.6}
+    except Exception as e:
+        ex["c1_fast_driver_default"] = {"error": repr(e)}
+    try:    # C2: exact FTL vs fast FTL on the same sequences, 1e4 trials (d = 5, T = 100), iterates compared on the device
+        z, y = engine.gen_sequences("gpath", 10_000, 100, 5)
+        dt, exr = wall(lambda: engine.exact_ftl_prefix_batch(z, y, want_actions=True))
+        sim = engine.simulate_batch(z, y, [1], [R2], full=True, trace=True)
+        same = bool((exr["actions"][:, :100].view(np.uint64) == sim["x_trace"][:, 0].view(np.uint64)).all())
+        ex["c2_exact_vs_fast_ftl_1e4_trials"] = {"wall_s": dt, "prefix_solves": 1_000_000, "value": 1e6 / dt, "unit": "exact prefix solves/s (host API, copies included)",
+                                                 "iterates_bit_identical_to_fast_ftl": same}
+        from online_convex_optimization_b200 import exact_ftl_driver as xd
+        dt, res = wall(lambda: xd.run_experiment())
+        ex["c2_exact_ftl_driver_default"] = {"wall_s": dt, "prefix_solves": 1.06e7, "value": 1.06e7 / dt, "unit": "exact prefix solves/s", "g_100": float(res["g_emp"][100])}
+        zz = z[:80] * 1.7          # outside the linear regime: the general interior-point solver
+        dt, g = wall(lambda: engine.exact_ftl_general_batch(zz, y[:80], norm="l2"))
+        ex["exact_general_solver"] = {"wall_s": dt, "prefix_solves": 8000, "value": 8000 / dt, "unit": "prefix solves/s (l2, d=5, rows scaled x1.7)",
+                                      "unconverged": int(g["status"].sum())}
+    except Exception as e:
+        ex["c2_error"] = repr(e)
+    try:    # SMART at T = 1e4 (fast_algorithms.py:118-164), d = 5, 2 thresholds
+        T, B = 10_000, 4096
+        zd, yd = engine.gen_sequences_device("gpath", B, T, 5, dtype=torch.float64)
+        th, et = [math.sqrt(2 * T), 60.0], [R2, R2]
+        ms, _ = timed(torch, lambda: engine.smart_batch_device(zd, yd, th, et, mode="linear"), 2)
+        ms2, _ = timed(torch, lambda: engine.smart_batch_device(zd[:592], yd[:592], th, et, mode="exact"), 1)
+        ex["smart_t1e4"] = {"linear_mode": {"value": B * T * 2 / (ms * 1e-3), "sequences": B, "ms": ms},
+                            "exact_mode": {"value": 592 * T * 2 / (ms2 * 1e-3), "sequences": 592, "ms": ms2},
+                            "unit": "trajectory-steps/s", "T": T, "d": 5, "thresholds": 2}
+        del zd, yd
+    except Exception as e:
+        ex["smart_t1e4"] = {"error": repr(e)}
+    try:    # float32 compute mode (algorithms.py:28-54) vs the float64 kernel on the same device-resident float32 sequences
+        T, B = 10_000, 65_536
+        zf, yf = engine.gen_sequences_device("iid", B, T, 5, key_a=2025, key_c0=13, dtype=torch.float32)
+        ms64, _ = timed(torch, lambda: engine.simulate_batch_device(zf, yf, [0, 1], [R2, R2]), 2)
+        ms32, _ = timed(torch, lambda: engine.simulate_batch_device(zf, yf, [0, 1], [R2, R2], compute="f32"), 2)
+        ex["fp32_mode_d5"] = {"f32_state": {"value": B * T * 2 / (ms32 * 1e-3), "ms": ms32}, "f64_state": {"value": B * T * 2 / (ms64 * 1e-3), "ms": ms64},
+                              "speedup_f32_over_f64": ms64 / ms32, "unit": "trajectory-steps/s", "sequences": B, "T": T, "variants": 2,
+                              "input_bytes_per_trajectory_step": 12}
+        del zf, yf
+    except Exception as e:
+        ex["fp32_mode_d5"] = {"error": repr(e)}
+    torch.cuda.empty_cache(); engine.release_scratch(local)
+    try:    # the FULL C4 job: 1e5 trials x T = 1e4 x d = 64 = 520 GB of sequences, generated AND simulated chunk by chunk
+        T, d, chunk, total = 10_000, 64, 14_208, 100_000
+        def job(mode):
+            best = None
+            for b0 in range(0, total, chunk):
+                nb = min(chunk, total - b0)
+                z, y = engine.gen_sequences_device("gpath", nb, T, d, key_a=0, key_c0=b0, dtype=torch.float64)
+                reg = engine.simulate_batch_device(z, y, [0], [R2], comparator=mode)
+                m = reg.max()
+                best = m if best is None else torch.maximum(best, m)
+                del z, y
+            return best
+        job_ms = {}
+        for mode in ("linear", "two_pass"):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); m = job(mode); e1.record(); torch.cuda.synchronize()
+            job_ms[mode] = (e0.elapsed_time(e1), float(m.item()))
+        ex["c4_full_job_1e5_trials"] = {m: {"wall_ms": v[0], "value": total * T / (v[0] * 1e-3), "max_regret": v[1]} for m, v in job_ms.items()}
+        ex["c4_full_job_1e5_trials"].update({"unit": "trajectory-steps/s", "includes": "on-device generation (fill kernel) of all 7 resident chunks + simulation",
+                                             "trials": total, "T": T, "d": d})
+    except Exception as e:
+        ex["c4_full_job_1e5_trials"] = {"error": repr(e)}
+    torch.cuda.empty_cache(); engine.release_scratch(local)
+    return ex
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -327,6 +529,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the brief c5 / c4 measurements appended to the default c3 line")
     ap.add_argument("--comparator", default="linear", choices=["linear", "two_pass"], help="c4 only")
+    ap.add_argument("--c5-runs", type=int, default=10_000_000, help="total runs of the strong-scaled C5 g(T) sweep (other_workloads)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.trials:
@@ -424,7 +627,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64-pipe", "achieved": kernel_steps_per_s * alg_ops / 1e9, "peak": fp64_peak / 1e9,
                          "unit": "Gop/s (non-fused fp64)", "frac": kernel_steps_per_s * alg_ops / fp64_peak,
-                         "traffic": ncu_traffic(kname, float(B) * A * T), "kernel": kname,
+                         "traffic": ncu_traffic(kname, float(B) * A * T), "traffic_from_profile": True, "kernel": kname,
                          "algorithmic_ops_per_trajectory_step": alg_ops,
                          "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)",
                          "ncu": ncu_utilisation(kname),
@@ -435,36 +638,39 @@ def main():
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_sweep_rate(wl, args.cpu_budget)
             line["cpu_baseline"] = {"value": v, "unit": "trajectory-steps/s", "cores": cores, "kind": "port", "sample": sample}
-    # the other BASELINE configurations, measured briefly in the same run (N = 1 default run only)
-    if world == 1 and args.workload == "c3" and not args.no_extras:
+    # ---- the north-star configuration (C5: 1e7 runs x T = 1e4 x d = 5 g(T) sweep, strong-scaled over the N ranks, one
+    # collective of the per-T curve) is measured at EVERY N; the remaining quoted workloads at N = 1
+    if args.workload == "c3" and not args.no_extras:
         del flush
         torch.cuda.empty_cache()
         engine.release_scratch(local)
         extras = {}
+        fp64_peak_all = engine.fp64_peak_ops(local)
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz = None
         try:
-            # 378,880 = 4 x 94,720 = 5 x 75,776: whole waves of resident threads at either 5 or 4 CTAs per SM
-            w5 = dict(WORKLOADS["c5"]); w5["trials"] = 378_880
-            for _ in range(2):
-                engine.regret_sweep_device("gpath", w5["trials"], w5["T"], w5["d"], w5["alg"], w5["eta"])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(2):
-                engine.regret_sweep_device("gpath", w5["trials"], w5["T"], w5["d"], w5["alg"], w5["eta"])
-            e1.record(); torch.cuda.synchronize()
-            r5 = 2 * w5["trials"] * w5["T"] / (e0.elapsed_time(e1) * 1e-3)
-            extras["c5_d5_ftrl_sweep"] = {"value": r5, "unit": "trajectory-steps/s", "trials": w5["trials"], "T": w5["T"],
-                                          "roofline": {"bound": "fp64-pipe", "achieved": r5 * 51 / 1e9, "peak": fp64_peak / 1e9,
-                                                       "unit": "Gop/s (non-fused fp64)", "frac": r5 * 51 / fp64_peak}}
-            engine.release_scratch(local)
-            sargs = argparse.Namespace(**vars(args)); sargs.steps, sargs.warmup = 3, 2
-            for mode in ("linear", "two_pass"):
-                sargs.comparator = mode
-                l4 = run_streamed(sargs, dict(WORKLOADS["c4"]), emit=False, init_dist=False)
-                extras["c4_d64_streamed_" + mode] = {k: l4[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "config")}
+            sm_mhz = float(subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"],
+                                          capture_output=True, text=True, timeout=5).stdout.strip())
+        except Exception:
+            pass
+        try:
+            c5 = run_c5(args, torch, dist, engine, odist, rank, world, local, dev, fp64_peak_all, sm_count, sm_mhz)
+            extras["c5_g_sweep_1e7_runs_strong_scaled"] = c5
         except Exception as ex:      # extras must never cost the headline number
-            extras["error"] = repr(ex)
-        line["other_workloads"] = extras
+            extras["c5_error"] = repr(ex)
+        engine.release_scratch(local)
+        if world == 1:
+            try:
+                extras.update(run_other_single_gpu(args, torch, engine, local, fp64_peak_all))
+                sargs = argparse.Namespace(**vars(args)); sargs.steps, sargs.warmup = 3, 2
+                for mode in ("linear", "two_pass"):
+                    sargs.comparator = mode
+                    l4 = run_streamed(sargs, dict(WORKLOADS["c4"]), emit=False, init_dist=False)
+                    extras["c4_d64_streamed_" + mode] = {k: l4[k] for k in ("value", "unit", "ms_per_step", "roofline", "e2e", "config")}
+            except Exception as ex:
+                extras["error"] = repr(ex)
+        if rank == 0:
+            line["other_workloads"] = extras
     if rank == 0:
         emit_line(line)
     if world > 1:

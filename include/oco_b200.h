@@ -205,8 +205,9 @@ OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo
  * pseudo-random doubles each (seed a); out[0] (uint64) = number of differing results (must be 0). */
 OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int64_t n_skip, int64_t n, void* out, int device);
 
-/* ---- scratch (the sweep kernel's row slab, scale tables) is allocated stream-ordered and kept cached
- * in the device's default memory pool between calls; this returns it to the driver. */
+/* ---- scratch (the sweep kernels' row slab, scale tables, staging buffers of the *_host calls) is allocated
+ * stream-ordered from a PRIVATE memory pool per device owned by this library and kept cached there between calls
+ * (the process-wide default pool and its release threshold are never touched); this returns it to the driver. */
 OCO_API int oco_release_scratch(int device);
 
 /* ---- roofline denominator for the generated-on-device kernels: measured issue rate of

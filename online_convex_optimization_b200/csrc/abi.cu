@@ -45,9 +45,9 @@ int make_variants(const int* alg_flag, const double* eta0, int A, Variants& v, E
     return OCO_OK;
 }
 
-struct DevBuf {           // stream-ordered scratch, freed on the same stream
+struct DevBuf {           // stream-ordered scratch from the library's own pool, freed on the same stream
     void* p = nullptr; cudaStream_t st = nullptr;
-    cudaError_t alloc(size_t n, cudaStream_t s) { st = s; return cudaMallocAsync(&p, n ? n : 8, s); }
+    cudaError_t alloc(size_t n, cudaStream_t s) { st = s; return oco::scratch_alloc(&p, n ? n : 8, s); }
     ~DevBuf() { if (p) cudaFreeAsync(p, st); }
     template <typename T> T* as() { return (T*)p; }
 };
@@ -73,19 +73,10 @@ struct StreamPair {
     ~StreamPair() { for (auto x : s) if (x) cudaStreamDestroy(x); }
 };
 
-// Keep stream-ordered scratch (the sweep kernel's slab can be tens of GB) cached in the device's
-// default memory pool across calls instead of returning it to the driver at every synchronise.
-void retain_pool_memory() {
-    static bool done[64] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    done[dev] = true;
-}
+// Scratch (the sweep kernels' row slab can be tens of GB) comes from a PRIVATE memory pool per device, owned by the
+// library (oco::scratch_pool, kernels_seeded.cu): it stays cached between calls without touching the release
+// threshold of the process-wide default pool, and oco_release_scratch() hands it back to the driver.
+void retain_pool_memory() {}
 
 int upload_keys(const uint64_t* keys, int64_t B, DevBuf& buf, cudaStream_t st, const uint64_t** out) {
     *out = nullptr;
@@ -441,6 +432,7 @@ OCO_API int oco_gen_sequences(int family, uint64_t key_a, uint64_t key_c0, const
     if (int rc = check_common(z, y, out_dtype, B, T, d, 1)) return rc;
     if (int rc = check_family(family, d, false)) return rc;
     if (family == OCO_FAM_SWITCH && block_len < 1) return fail(OCO_ERR_VALUE, "block_len must be >= 1");
+    if (T > 0x7fffffff) return fail(OCO_ERR_VALUE, "T must be < 2^31");
     if (B == 0 || T == 0) return OCO_OK;
     cudaStream_t st = (cudaStream_t)stream;
     DevBuf kb; const uint64_t* kd = nullptr;
@@ -621,9 +613,7 @@ OCO_API int oco_rng_probe_host(int what, uint64_t a, uint64_t b, uint64_t c, int
 OCO_API int oco_release_scratch(int device) {
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     CU(cudaDeviceSynchronize());
-    cudaMemPool_t pool;
-    CU(cudaDeviceGetDefaultMemPool(&pool, device));
-    CU(cudaMemPoolTrimTo(pool, 0));
+    CU(oco::scratch_trim());
     return OCO_OK;
 }
 

@@ -149,7 +149,9 @@ template <int D>
 __device__ __forceinline__ void gpath_row2(const ZigTab2& tb, Pcg64& s, const PcgInc& inc, double (&z)[D]) {
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = zig_normal2(tb, s, inc);
-    const double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+    double nrm;
+    if constexpr (D == 1) nrm = fabs(z[0]);
+    else nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
     const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
@@ -215,7 +217,9 @@ template <int D>
 __device__ __forceinline__ void gpath_row_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc, double (&z)[D]) {
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = zig_normal_la(tb, g, inc);
-    const double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+    double nrm;
+    if constexpr (D == 1) nrm = fabs(z[0]);     // sqrt(fl(z*z)) == |z| for 1 < |z| < 1e145, and both are <= 1 together otherwise
+    else nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
     const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
@@ -258,15 +262,31 @@ static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint
 }
 
 // ---------------------------------------------------------------- the kernel
+// Rows come back from the slab through a per-thread ring of asynchronous copies (cp.async, SASS LDGSTS): row t + 3 is
+// requested at the end of step t and lands in shared memory without touching a register, so no scoreboard wait can be
+// scheduled next to the request (a register prefetch was rotated by the compiler into "load, then copy at the end of
+// the same step": 26 % of all stall samples on that copy).  Every thread reads only the slots it filled itself.
+constexpr int kRing = 4;
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 #ifndef OCO_GSWEEP_MIN_BLOCKS
 #define OCO_GSWEEP_MIN_BLOCKS 5
 #endif
+#ifndef OCO_GSWEEP_MIN_BLOCKS_NF
+#define OCO_GSWEEP_MIN_BLOCKS_NF 4          // several FTRL variants per thread: more registers, fewer resident CTAs
+#endif
 
 template <int D, int NFTL, int NF>
-__global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : 4)) gsweep_kernel(const SweepArgs p) {
-    static_assert(D >= 2 && D <= 8, "d = 1 has the exact one-pass comparator of sweep_kernel");
+__global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : OCO_GSWEEP_MIN_BLOCKS_NF)) gsweep_kernel(const SweepArgs p) {
+    static_assert(D >= 1 && D <= 8, "thread-per-sequence kernel: theta lives in registers");
     __shared__ ZigTab2 tb;
     __shared__ double red[kSweepBlock / 32][3];
+    __shared__ double ring[kRing][D][kSweepBlock];              // [slot][coordinate][thread]: conflict-free LDS.64
     zig_tab2_load(tb);
     const int T = p.T, A = p.plan.A, tid = threadIdx.x;
     const int groups = p.plan.groups;
@@ -317,14 +337,27 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
         for (int j = 0; j < D; ++j) th2l[j] = 0.0;
         const double* __restrict__ tp = p.tab + (int64_t)gB * T * NF;
         const bool do_ftl = NFTL > 0 && gB == 0 && p.plan.n_ftl > 0;
+        // d = 1: the comparator -(1/sqrt(th*th))*th = -th*fl(1/|th|) is one of +-1, +-w (w = 1 - 2^-53) or 0, so the
+        // comparator losses of ALL variants are among four running sums that depend on the sequence only, accumulated
+        // in the reference's order (fast_algorithms.py:69-76): exact, and no second pass (sweep_impl.cuh)
+        double cand[4] = {0.0, 0.0, 0.0, 0.0};                  // sum |c*z - y| for c = +1, -1, +w, -w
+        const double kW = __longlong_as_double(0x3fefffffffffffffLL);
 
         // the row and the FTRL scales of step t are fetched at the END of step t - 1 into the registers step t
         // reads them from (no copy the compiler could sink to the loop end): a whole generation step hides the HBM latency
-        double zc[D], scn[NF];
-#pragma unroll
-        for (int j = 0; j < D; ++j) zc[j] = (doB && T > 0) ? __ldcg(zr + j * kSweepBlock) : 0.0;
+        double scn[NF];
 #pragma unroll
         for (int k = 0; k < NF; ++k) scn[k] = (doB && T > 0) ? __ldg(tp + k) : 0.0;
+        if (doB) {                                              // rows 0 .. kRing-2 of the sequence to play: one group per row
+#pragma unroll
+            for (int i = 0; i < kRing - 1; ++i) {
+                if (i < T) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) cp_async8(&ring[i][j][tid], zr + ((int64_t)i * D + j) * kSweepBlock);
+                }
+                cp_async_commit();
+            }
+        }
 
         for (int t = 0; t < T; ++t) {
             // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
@@ -337,8 +370,77 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             }
             // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
             if (doB) {
-                const double (&z)[D] = zc;
+                cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
+                double z[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = ring[t & (kRing - 1)][j][tid];
                 const double y = lab.next(t, incB);
+                if constexpr (D == 1) {
+                    // (d = 1 keeps theta itself in th2*: one shared hz = 0.5*z per step beats halving NF scales)
+                    const double z0 = z[0], hz0 = 0.5 * z0;
+                    const double pw = z0 * kW;                      // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
+                    cand[0] = cand[0] + fabs(z0 - y);
+                    cand[1] = cand[1] + fabs(z0 + y);
+                    cand[2] = cand[2] + fabs(pw - y);
+                    cand[3] = cand[3] + fabs(pw + y);
+                    if (NFTL > 0 && do_ftl) {
+                        // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal;
+                        // th == 0 plays -0.0 instead of 0.0 (z*x is a zero either way and df = -y exactly)
+                        const double n2 = th2l[0] * th2l[0];
+                        double rc = rcp_inrange(th2l[0]);           // garbage unless 1e-290 <= n2 <= 1e290
+                        if (!(n2 >= 1e-290 && n2 <= 1e290)) rc = (n2 == 0.0) ? 1.0 : 1.0 / sqrt(n2);
+                        const double x = -fabs(rc) * th2l[0];
+                        const double df = z0 * x - y;
+                        Sl = Sl + fabs(df);
+                        const int sgn = __double2hiint(df) & 0x80000000;
+                        const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
+                        if (fabs(df) > 0.0) th2l[0] = th2l[0] + gz;         // zero / NaN diff: no step (fast_algorithms.py:27-34)
+                    }
+                    // the NF FTRL variants are independent chains: all actions first, then the projections, voted per HALF
+                    // (variants are usually passed in eta0 order: the small-eta half almost never projects, the large-eta half
+                    // almost always), branch-free reciprocals the scheduler can interleave, then all the steps
+                    double x1[NF], n2v[NF];
+                    constexpr int H = NF >= 4 ? NF / 2 : NF;
+                    int top0 = 0, top1 = 0;                         // max over the half of the high word of n2 (n2 >= 0 or NaN)
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {
+                        x1[k] = scn[k] * th2r[k][0];
+                        n2v[k] = x1[k] * x1[k];
+                        if (k < H) top0 = max(top0, __double2hiint(n2v[k])); else top1 = max(top1, __double2hiint(n2v[k]));
+                    }
+                    auto project_range = [&](int lo, int hi, int top) {
+                        if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
+                            if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
+#pragma unroll
+                                for (int k = 0; k < NF; ++k) {
+                                    if (k >= lo && k < hi) {
+                                        double xx[1] = {x1[k]};
+                                        project_unit_ball<1>(xx, n2v[k], mask);
+                                        x1[k] = xx[0];
+                                    }
+                                }
+                            } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
+#pragma unroll
+                                for (int k = 0; k < NF; ++k) {
+                                    if (k >= lo && k < hi) {
+                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
+                                        if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
+                                    }
+                                }
+                            }
+                        }
+                    };
+                    project_range(0, H, top0);
+                    if (H < NF) project_range(H, NF, top1);
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {
+                        const double df = z0 * x1[k] - y;
+                        Sr[k] = Sr[k] + fabs(df);
+                        const int sgn = __double2hiint(df) & 0x80000000;
+                        const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
+                        if (fabs(df) > 0.0) th2r[k][0] = th2r[k][0] + gz;
+                    }
+                } else {
                 const int yhi = __double2hiint(y);
                 if (NFTL > 0 && do_ftl) {
                     // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
@@ -376,10 +478,15 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                             th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
                     } else zero_df = true;
                 }
-                tp += NF; zr += D * kSweepBlock;
-                if (t + 1 < T) {
+                }
+                tp += NF;
+                if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
 #pragma unroll
-                    for (int j = 0; j < D; ++j) zc[j] = __ldcg(zr + j * kSweepBlock);
+                    for (int j = 0; j < D; ++j)
+                        cp_async8(&ring[(t + kRing - 1) & (kRing - 1)][j][tid], zr + ((int64_t)(t + kRing - 1) * D + j) * kSweepBlock);
+                }
+                cp_async_commit();
+                if (t + 1 < T) {
 #pragma unroll
                     for (int k = 0; k < NF; ++k) scn[k] = __ldg(tp + k);
                 }
@@ -399,10 +506,20 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 for (int j = 1; j < D; ++j) n2 = n2 + th2[j] * th2[j];
                 const double nth = 0.5 * sqrt(n2);              // ||theta_T||
                 cum = 0.5 * S;
-                if (ok < 0 && !zero_df && !p.force_second_pass) {
+                if constexpr (D == 1) {
+                    // a == 0 (theta == 0): every term is |+-0 - y| = 1, the sum is T exactly
+                    double a1[1], C = 0.0; bool found = true;
+                    ftl_action<1>(th2, a1);
+                    if (a1[0] == 1.0) C = cand[0]; else if (a1[0] == -1.0) C = cand[1];
+                    else if (a1[0] == kW) C = cand[2]; else if (a1[0] == -kW) C = cand[3];
+                    else if (a1[0] == 0.0) C = (double)T; else found = false;   // not reachable for finite theta
+                    if (found && !p.force_second_pass) { comp = 0.5 * C; reg = cum - comp; return; }
+                } else if (ok < 0 && !zero_df && !p.force_second_pass) {
                     comp = halfT - nth;
                     reg = (cum - halfT) + nth;
-                } else {                                        // literal second pass (exact)
+                    return;
+                }
+                {                                               // literal second pass (exact)
                     double a[D];
                     ftl_action<D>(th2, a);
                     const uint64_t ka = p.keys ? p.keys[2 * bB] : p.key_a;
@@ -490,13 +607,14 @@ static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
     if (per_cta > 0) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += scratch_cached_free_bytes();     // what the library's own pool holds idle is reusable by this call
             const int64_t fit = (int64_t)((free_b / 10) * 7 / per_cta);
             if (fit < 1) return cudaErrorMemoryAllocation;
             grid = std::min<int64_t>(grid, fit);
         }
     }
     void* slab = nullptr;
-    e = cudaMallocAsync(&slab, (size_t)grid * per_cta + 256, st);
+    e = scratch_alloc(&slab, (size_t)grid * per_cta + 256, st);
     if (e != cudaSuccess) return e;
     a.slab_z = slab; a.slab_y = nullptr;
     kern<<<(unsigned)grid, kSweepBlock, 0, st>>>(a);

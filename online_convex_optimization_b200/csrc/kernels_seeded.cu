@@ -10,7 +10,65 @@
 //  rng_probe_kernel                 known-answer probes of the device generator
 #include "sweep_impl.cuh"
 
+#include <mutex>
+
 namespace oco {
+
+// ------------------------------------------------------------------ private scratch pool (one per device)
+namespace {
+constexpr int kMaxDev = 64;
+cudaMemPool_t g_pool[kMaxDev];
+std::once_flag g_pool_once[kMaxDev];
+cudaError_t g_pool_err[kMaxDev];
+
+cudaMemPool_t scratch_pool(int dev, cudaError_t* err) {
+    std::call_once(g_pool_once[dev], [dev]() {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        g_pool_err[dev] = cudaMemPoolCreate(&g_pool[dev], &props);
+        if (g_pool_err[dev] == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            g_pool_err[dev] = cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    });
+    *err = g_pool_err[dev];
+    return g_pool[dev];
+}
+}  // namespace
+
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDev) return cudaMallocAsync(p, bytes, st);
+    cudaMemPool_t pool = scratch_pool(dev, &e);
+    if (e != cudaSuccess) return e;
+    return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
+
+cudaError_t scratch_trim() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= kMaxDev) return e;
+    cudaMemPool_t pool = scratch_pool(dev, &e);
+    if (e != cudaSuccess) return e;
+    return cudaMemPoolTrimTo(pool, 0);
+}
+
+size_t scratch_cached_free_bytes() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= kMaxDev) return 0;
+    cudaMemPool_t pool = scratch_pool(dev, &e);
+    if (e != cudaSuccess) return 0;
+    unsigned long long reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) return 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) return 0;
+    return reserved > used ? (size_t)(reserved - used) : 0;
+}
 
 // One 256-thread block per variant; thread l folds chunks l, l + 256, ... in order, then a fixed shared-memory
 // tree: the association order depends only on (nblocks), so the statistics are reproducible run to run.
@@ -97,8 +155,10 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
     }
     a.debug_phase = 0;
     if (const char* e = getenv("OCO_GSWEEP_DEBUG")) a.debug_phase = atoi(e);     // timing experiments: one phase only
-    if (family == FAM_GPATH && d >= 2 && comparator_mode == 1) {
-        // single-pass comparator (no second pass over the rows) + software-pipelined generate / play: gsweep_impl.cuh
+    const char* legacy = getenv("OCO_SWEEP_D1_LEGACY");                          // A/B knob: round-1 kernel for d = 1
+    if (family == FAM_GPATH && ((d == 1 && !(legacy && legacy[0] == '1')) || (d >= 2 && comparator_mode == 1))) {
+        // software-pipelined generate / play kernel (gsweep_impl.cuh): d = 1 keeps the exact candidate-sum comparator
+        // (either mode, bit-exact); d >= 2 with OCO_COMPARATOR_LINEAR uses T/2 - ||theta_T|| (no second pass over the rows)
         return d <= 3 ? launch_gsweep_lo(a, d, st) : launch_gsweep_hi(a, d, st);
     }
     if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);

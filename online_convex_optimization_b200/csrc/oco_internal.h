@@ -16,6 +16,13 @@ enum Family {                      // sequence families
     FAM_SWITCH = 4,                // sequence_generation.py:36-47
 };
 
+// ---- scratch: a private stream-ordered memory pool per device, owned by the library (kernels_seeded.cu).
+// Nothing is released back to the driver between calls (release threshold = max) -- the sweep kernels' row slab is
+// tens of GB and re-reserving it costs more than a short sweep -- but the process-wide DEFAULT pool is never touched.
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st);
+cudaError_t scratch_trim();                      // current device: give cached scratch back to the driver
+size_t scratch_cached_free_bytes();              // current device: reserved by the pool but not in use (reusable by the next call)
+
 struct Variants {                  // passed by value to kernels
     int A;
     int alg_flag[kMaxVariants];    // 0 = FTRL, non-zero = FTL (fast_algorithms.py:100-103)
@@ -51,7 +58,7 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
                          double* regret, double* cum, double* comp, double* partials, int comparator_mode, cudaStream_t st);
 cudaError_t launch_sweep_gpath(const struct SweepArgs& a, int d, cudaStream_t st);
 // g-path, 2 <= d <= 5, single-pass comparator, rows regenerated instead of parked in HBM (gsweep_impl.cuh)
-cudaError_t launch_gsweep_lo(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 2, 3
+cudaError_t launch_gsweep_lo(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 1, 2, 3
 cudaError_t launch_gsweep_hi(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 4, 5
 cudaError_t launch_sweep_iid(const struct SweepArgs& a, int d, cudaStream_t st);
 int sweep_gpath_blocks(int64_t n_runs);

@@ -417,6 +417,7 @@ static cudaError_t launch_sweep_cfg(SweepArgs a, cudaStream_t st) {
     {   // never ask for more than ~70 % of the free device memory: fewer resident CTAs, same result
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            free_b += scratch_cached_free_bytes();     // what the library's own pool holds idle is reusable by this call
             const size_t per_cta = (size_t)a.T * D * kSweepBlock * sizeof(E) + (size_t)((a.T + 31) / 32) * kSweepBlock * 4 + 1;
             const int64_t fit = (int64_t)((free_b / 10) * 7 / per_cta);
             if (fit < 1) return cudaErrorMemoryAllocation;
@@ -426,7 +427,7 @@ static cudaError_t launch_sweep_cfg(SweepArgs a, cudaStream_t st) {
     const size_t zbytes = (size_t)grid * a.T * D * kSweepBlock * sizeof(E);
     const size_t ybytes = (size_t)grid * ((a.T + 31) / 32) * kSweepBlock * sizeof(uint32_t);
     void* slab = nullptr;
-    e = cudaMallocAsync(&slab, zbytes + ybytes + 256, st);
+    e = scratch_alloc(&slab, zbytes + ybytes + 256, st);
     if (e != cudaSuccess) return e;
     a.slab_z = slab;
     a.slab_y = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(slab) + ((zbytes + 255) / 256) * 256);

@@ -239,14 +239,21 @@ def _dptr(t) -> C.c_void_p:
     return C.c_void_p(None if t is None else t.data_ptr())
 
 
-def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, comparator: str = "two_pass", compute: str = "f64"):
-    """z (B,T,d), y (B,T): contiguous CUDA tensors (float32 or float64).  Returns CUDA tensors."""
-    torch = _torch()
+def _check_device_inputs(torch, z, y):
+    """The kernels read raw pointers: z (B,T,d) and y (B,T) must be contiguous CUDA tensors of ONE float dtype on one device."""
     if z.dtype != y.dtype or z.dtype not in (torch.float32, torch.float64):
         raise ValueError("z and y must both be float32 or float64")
     if not (z.is_cuda and y.is_cuda and z.is_contiguous() and y.is_contiguous()):
         raise ValueError("z and y must be contiguous CUDA tensors")
-    B, T, d = z.shape
+    if z.device != y.device or z.dim() != 3 or y.dim() != 2 or tuple(y.shape) != tuple(z.shape[:2]):
+        raise ValueError("need z (B,T,d) and y (B,T) on the same device")
+    return z.shape
+
+
+def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, comparator: str = "two_pass", compute: str = "f64"):
+    """z (B,T,d), y (B,T): contiguous CUDA tensors (float32 or float64).  Returns CUDA tensors."""
+    torch = _torch()
+    B, T, d = _check_device_inputs(torch, z, y)
     af, et = _variants(alg_flags, eta0s)
     A = af.size
     reg = torch.empty((B, A), dtype=torch.float64, device=z.device)
@@ -265,7 +272,7 @@ def simulate_batch_device(z, y, alg_flags, eta0s, *, full: bool = False, compara
 
 def smart_batch_device(z, y, theta_threshs, eta0s, *, mode: str = "exact"):
     torch = _torch()
-    B, T, d = z.shape
+    B, T, d = _check_device_inputs(torch, z, y)
     th = np.ascontiguousarray(np.atleast_1d(theta_threshs), dtype=np.float64)
     et = np.ascontiguousarray(np.atleast_1d(eta0s), dtype=np.float64)
     A = th.size

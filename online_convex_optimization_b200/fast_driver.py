@@ -54,6 +54,8 @@ def _regrets_for_T(stream_builder, T: int, theta_emp: float, runs: int, replicat
                    compute: str = "f64") -> np.ndarray:
     """Per-sequence regrets, shape (runs, replicates, 4) in ALGO_KEYS order, for one horizon."""
     samplers = [stream_builder(run_seed=base_seed + 2025 * (run + 1)) for run in range(runs)]
+    if runs <= 0 or replicates <= 0:                    # the reference's loops simply do not execute: empty statistics
+        return np.zeros((max(runs, 0), max(replicates, 0), 4))
     spec = getattr(samplers[0], "spec", None)
     B = runs * replicates
     thresholds = [math.sqrt(2 * T), float(theta_emp)]

@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(kStreamBlock) sim_stream_f32_kernel(const Stre
     }
 }
 
+static cudaError_t launch_stream_async_f32_any(const StreamArgs& a, int d, cudaStream_t st, bool* done);
+
 cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64_t T, int d,
                                   const Variants& v, const double* scale_tab,
                                   double* regret, double* cum, double* comp, double* theta_final, double* x_last,
@@ -195,6 +197,11 @@ cudaError_t launch_sim_stream_f32(const void* z, const void* y, int64_t B, int64
     a.comparator_mode = 0;
     a.z = z; a.y = y; a.B = B; a.T = T; a.tab = scale_tab; a.comparator = nullptr;
     a.regret = regret; a.cum = cum; a.comp = comp; a.theta_final = theta_final; a.x_last = x_last; a.x_trace = nullptr; a.v = v;
+    {   // aligned shapes: the cp.async-staged float kernel; anything else: the direct-load kernel below
+        bool done = false;
+        const cudaError_t e = launch_stream_async_f32_any(a, d, st, &done);
+        if (done) return e;
+    }
     const dim3 grid((unsigned)((B + kStreamBlock - 1) / kStreamBlock), (unsigned)v.A);
     switch (d) {
     case 1: sim_stream_f32_kernel<1><<<grid, kStreamBlock, 0, st>>>(a); break;
@@ -485,12 +492,222 @@ __global__ void __launch_bounds__(kAWarps * 32, (AV == 1 ? 4 : 3)) sim_stream_as
     }
 }
 
+// ------------------------------------------------------------------ float32 compute mode on the staged data path
+// algorithms.py:28-54 (the reference's NumPy twin: float32 theta / x, float64 loss accumulators), tolerance 1e-5
+// (north_star).  Same cp.async tile pipeline as sim_stream_async_kernel on float32 rows (24 B per sequence-step at
+// d = 5); the per-step arithmetic runs on the fp32 pipes with fused multiply-adds (the tolerance allows any summation
+// order for the dot products; sqrt and 1/n stay IEEE float32 operations, as NumPy's are: on the adversarial
+// families (z = e_1, labels +-1) the played action is exactly +-1 or +-(1 - 2^-24) and q - y is exactly 0 on half
+// of the rounds -- an approximate reciprocal would turn those into spurious gradient steps).  Only the two loss sums are
+// float64 (cum_loss is float64 in the reference, algorithms.py:35,45; comp_loss is a pairwise float32 np.sum there,
+// which a float64 running sum matches to 1e-7).  AV variants share every staged row.
+template <int D, int AV>
+__global__ void __launch_bounds__(kAWarps * 32, 4) sim_stream_async_f32_kernel(const StreamArgs p) {
+    typedef AsyncTile<D, float> L;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b0 = ((int64_t)blockIdx.x * kAWarps + wib) * 32;
+    if (b0 >= p.B) return;
+    const int64_t b = b0 + lane;
+    const bool active = b < p.B;
+    const int nseq = (int)((p.B - b0) < 32 ? (p.B - b0) : 32);
+    const int A = p.v.A;
+    const int v0 = blockIdx.y * AV;
+    const int nv = min(AV, A - v0);
+    const int64_t T = p.T;
+    const unsigned char* __restrict__ zw = (const unsigned char*)p.z + b0 * T * D * L::ES;
+    const unsigned char* __restrict__ yw = (const unsigned char*)p.y + b0 * T * L::ES;
+    unsigned char* wsm = smem_raw + (size_t)wib * 2 * L::STAGE;
+    const int ntiles = (int)(T / kAT);
+
+    const int cg = lane / L::GS, coff = lane % L::GS;
+    const bool cz = coff < L::ZB / 16, cvalid = coff < L::NP;
+    const int ctile = cz ? kAT * D * L::ES : kAT * L::ES;
+    const int64_t cstep = (int64_t)L::SPI * (cz ? T * D * L::ES : T * L::ES);
+    const unsigned char* csrc = cz ? zw + (int64_t)cg * T * D * L::ES + coff * 16
+                                   : yw + (int64_t)cg * T * L::ES + (coff - L::ZB / 16) * 16;
+    const uint32_t cdst = (uint32_t)__cvta_generic_to_shared(wsm) + cg * L::REC + coff * 16;
+    auto stage_tile = [&](int tile, int st) {
+        const unsigned char* src = csrc + (int64_t)tile * ctile;
+        uint32_t dst = cdst + st * L::STAGE;
+#pragma unroll
+        for (int i = 0; i < L::GS; ++i) {
+            if (cvalid && i * L::SPI + cg < nseq) cp_async16_s(dst, src);
+            src += cstep; dst += L::SPI * L::REC;
+        }
+        cp_async_commit();
+    };
+
+    float th[AV][D], act[AV][D], xl[AV][D];
+    double S[AV], C[AV];
+    bool is_ftrl[AV];
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+        S[v] = 0.0; C[v] = 0.0; is_ftrl[v] = v < nv && p.v.alg_flag[v0 + v] == 0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) { th[v][j] = 0.0f; xl[v][j] = 0.0f; act[v][j] = 0.0f; }
+    }
+    auto ftl_act = [&](const float (&t_)[D], float (&x)[D]) {    // algorithms.py:13-15
+        float n2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) n2 = __fmaf_rn(t_[j], t_[j], n2);
+        const float n = sqrtf(n2);                                   // np.linalg.norm: sqrt(x.dot(x)), IEEE float32
+        const float sc = n == 0.0f ? 0.0f : -(1.0f / n);             // -(1.0 / n): IEEE float32 division
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = sc * t_[j];
+    };
+    auto row_step = [&](int pass, int64_t t, const float (&z)[D], float y) {
+        if (pass == 0) {
+            const double* trow = p.tab + t * A + v0;
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                if (v < nv) {
+                    float x[D];
+                    if (is_ftrl[v]) {                             // algorithms.py:17-21
+                        const float sc = (float)__ldg(trow + v);
+                        float n2 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < D; ++j) { x[j] = sc * th[v][j]; n2 = __fmaf_rn(x[j], x[j], n2); }
+                        if (n2 > 1.0f) {                              // n > 1.0 needs n2 > 1; n2 barely above 1 gives n == 1, inv == 1
+                            const float inv = 1.0f / sqrtf(n2);
+#pragma unroll
+                            for (int j = 0; j < D; ++j) x[j] = x[j] * inv;
+                        }
+                    } else {
+                        ftl_act(th[v], x);
+                    }
+                    float q = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) { q = __fmaf_rn(z[j], x[j], q); xl[v][j] = x[j]; }
+                    const float df = q - y;                        // q, y in [-1, 1]: the float subtraction is exact to 1 ulp
+                    S[v] = S[v] + (double)fabsf(df);
+                    const float g = df > 0.0f ? 0.5f : (df < 0.0f ? -0.5f : 0.0f);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) th[v][j] = __fmaf_rn(g, z[j], th[v][j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < AV; ++v) {
+                if (v < nv) {
+                    float q = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) q = __fmaf_rn(z[j], act[v][j], q);
+                    C[v] = C[v] + (double)fabsf(q - y);
+                }
+            }
+        }
+    };
+    auto run_pass = [&](int pass) {
+        if (ntiles > 0) stage_tile(0, 0);
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int st = tile & 1;
+            if (tile + 1 < ntiles) { stage_tile(tile + 1, st ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncwarp();
+            if (active) {
+                const unsigned char* rec = wsm + st * L::STAGE + lane * L::REC;
+                float yv[kAT];
+                {
+                    const uint4 yb4 = *reinterpret_cast<const uint4*>(rec + L::ZB);
+                    const float* ye = reinterpret_cast<const float*>(&yb4);
+#pragma unroll
+                    for (int r = 0; r < kAT; ++r) yv[r] = ye[r];
+                }
+#pragma unroll
+                for (int g = 0; g < kAT / L::RG; ++g) {
+                    uint4 zbuf[L::GV];
+#pragma unroll
+                    for (int i = 0; i < L::GV; ++i) zbuf[i] = *reinterpret_cast<const uint4*>(rec + (g * L::GV + i) * 16);
+                    const float* ze = reinterpret_cast<const float*>(zbuf);
+#pragma unroll
+                    for (int r = 0; r < L::RG; ++r) {
+                        float z[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) z[j] = ze[r * D + j];
+                        row_step(pass, (int64_t)tile * kAT + g * L::RG + r, z, yv[g * L::RG + r]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (active) {
+            const float* zb = reinterpret_cast<const float*>(zw) + (int64_t)lane * T * D;
+            const float* yb = reinterpret_cast<const float*>(yw) + (int64_t)lane * T;
+            for (int64_t t = (int64_t)ntiles * kAT; t < T; ++t) {
+                float z[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) z[j] = zb[t * D + j];
+                row_step(pass, t, z, yb[t]);
+            }
+        }
+    };
+    run_pass(0);
+#pragma unroll
+    for (int v = 0; v < AV; ++v) ftl_act(th[v], act[v]);          // comparator: FTL action of the final theta (algorithms.py:50)
+    run_pass(1);
+    if (!active) return;
+#pragma unroll
+    for (int v = 0; v < AV; ++v) {
+        if (v < nv) {
+            const int64_t o = b * A + v0 + v;
+            const double cum = 0.5 * S[v], comp = 0.5 * C[v];
+            if (p.regret) p.regret[o] = cum - comp;
+            if (p.cum) p.cum[o] = cum;
+            if (p.comp) p.comp[o] = comp;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (p.theta_final) p.theta_final[o * D + j] = (double)th[v][j];
+                if (p.x_last) p.x_last[o * D + j] = (double)xl[v][j];
+            }
+        }
+    }
+}
+
 // every 16-byte piece must be 16-byte aligned in global memory
 template <int D, typename TIN>
 static bool async_eligible(const StreamArgs& a) {
     const size_t es = sizeof(TIN);
     return ((uintptr_t)a.z % 16 == 0) && ((uintptr_t)a.y % 16 == 0) && ((size_t)a.T * D * es) % 16 == 0 &&
            ((size_t)a.T * es) % 16 == 0 && (kAT * D * es) % 16 == 0 && (kAT * es) % 16 == 0 && a.T >= kAT;
+}
+
+template <int D>
+static cudaError_t launch_stream_async_f32_d(const StreamArgs& a, cudaStream_t st, bool* done) {
+    typedef AsyncTile<D, float> L;
+    *done = false;
+    if (!async_eligible<D, float>(a)) return cudaSuccess;
+    *done = true;
+    const int A = a.v.A;
+    const int64_t nwarps = (a.B + 31) / 32;
+    const unsigned gx = (unsigned)((nwarps + kAWarps - 1) / kAWarps);
+    const size_t smem = (size_t)kAWarps * 2 * L::STAGE;
+    cudaError_t e;
+    if (A == 1) {
+        auto kern = sim_stream_async_f32_kernel<D, 1>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<dim3(gx, 1), kAWarps * 32, smem, st>>>(a);
+    } else {
+        auto kern = sim_stream_async_f32_kernel<D, 4>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<dim3(gx, (unsigned)((A + 3) / 4)), kAWarps * 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+static cudaError_t launch_stream_async_f32_any(const StreamArgs& a, int d, cudaStream_t st, bool* done) {
+    switch (d) {
+    case 1: return launch_stream_async_f32_d<1>(a, st, done);
+    case 2: return launch_stream_async_f32_d<2>(a, st, done);
+    case 3: return launch_stream_async_f32_d<3>(a, st, done);
+    case 4: return launch_stream_async_f32_d<4>(a, st, done);
+    case 5: return launch_stream_async_f32_d<5>(a, st, done);
+    case 6: return launch_stream_async_f32_d<6>(a, st, done);
+    case 7: return launch_stream_async_f32_d<7>(a, st, done);
+    case 8: return launch_stream_async_f32_d<8>(a, st, done);
+    default: *done = false; return cudaSuccess;
+    }
 }
 
 template <int D, int AV, typename TIN>

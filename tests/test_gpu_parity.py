@@ -489,3 +489,22 @@ def test_smart_full_length_T1e4(eng):
     from online_convex_optimization_b200 import fast_algorithms as fa
     assert abs(fa.simulate_SMART(z[8], y[8]) - wr[8, 3]) <= REL * max(1.0, abs(wr[8, 3]))
     assert abs(fa.simulate_empirical_g_SMART(z[0], y[0], 15.0) - wr[0, 1]) <= REL * max(1.0, abs(wr[0, 1]))
+
+
+def test_float32_mode_small_d_knife_edges(eng):
+    """float32 mode against the reference's algorithms.py on d = 1 / 2 / 8 g-path rows cast to float32 (fixtures made by
+    running the reference, tests/golden/driver32_stats.json): at d = 1 a third of the rows have |z| = 1 exactly and
+    q - y is 0 or one float32 ulp, so only IEEE float32 sqrt / divide reproduce the reference's gradient steps."""
+    import json, os
+    from conftest import GOLDEN
+    recs = json.load(open(os.path.join(GOLDEN, "driver32_stats.json")))["f32_small_d"]
+    n = 0
+    for rec in recs:
+        z, y = make_sequence(rec["spec"])
+        z32, y32 = np.asarray(z, dtype=np.float32)[None], np.asarray(y, dtype=np.float32)[None]
+        for key, v in rec["results"].items():
+            flag = int(key[3]); eta = float(key.split("eta")[1]); want = hexf(v)
+            got = eng.simulate_batch(z32, y32, [flag], [eta], compute="f32")[0, 0]
+            assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (rec["spec"], key, got, want)
+            n += 1
+    assert n == 24

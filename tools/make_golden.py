@@ -258,6 +258,17 @@ def exact_det():
 def driver32_stats():
     dr = load_ref_module("driver")
     res = {}
+    # float32 twin (algorithms.py:28-54) on knife-edge shapes: d = 1 clipped rows (|z| = 1 on a third of the rounds, the
+    # projected action is +-1 or +-(1 - 2^-24), q - y is exactly 0 or one ulp) and d = 8
+    res["f32_small_d"] = []
+    for (b, T, r, d) in [(7, 300, 0, 1), (7, 257, 3, 1), (3, 200, 2, 8), (5, 129, 1, 2)]:
+        z, y = gpath(b, T, r, d)
+        zf, yf = z.astype(np.float32), y.astype(np.float32)
+        rec = {"spec": {"family": "gpath", "base_seed": b, "T": T, "run": r, "d": d}, "results": {}}
+        for flag in (0, 1):
+            for eta in (R2, 0.25, 4.0):
+                rec["results"][f"alg{flag}_eta{eta!r}"] = float(alg32.simulate_alg(zf, yf, flag, eta)).hex()
+        res["f32_small_d"].append(rec)
     small_grid = np.array([100, 200, 300])
     g32 = alg32.empirical_worst_case_thresholds(small_grid, runs=40, base_seed=0)
     res["g_emp_runs40"] = {str(k): float(v).hex() for k, v in g32.items()}

@@ -92,9 +92,11 @@ int check_family(int family, int d, bool fused) {
     if (fused) {
         if (family > OCO_FAM_NOISY) return fail(OCO_ERR_VALUE, "fused sweep supports the seeded families only (got %d)", family);
         if (d > 5) return fail(OCO_ERR_VALUE, "fused sweep supports d <= 5 (got %d); generate + simulate instead", d);
+    } else if (family == OCO_FAM_GPATH) {
+        if (d > 128) return fail(OCO_ERR_VALUE, "g-path generator supports d <= 128 (got %d)", d);
     } else if (family <= OCO_FAM_NOISY) {
         const bool ok = (d >= 1 && d <= 5) || d == 8 || d == 16 || d == 32 || d == 64;
-        if (!ok) return fail(OCO_ERR_VALUE, "generator supports d in {1..5, 8, 16, 32, 64} (got %d)", d);
+        if (!ok) return fail(OCO_ERR_VALUE, "iid generators support d in {1..5, 8, 16, 32, 64} (got %d)", d);
     }
     return OCO_OK;
 }

@@ -246,6 +246,12 @@ cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint6
         else fill_pattern_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(family, B, T, d, block_len, (double*)z, (double*)y);
         return cudaGetLastError();
     }
+    {   // g-path: one WARP per sequence (jump-ahead PCG64, coalesced stores), any d <= 128; OCO_FILL_LEGACY=1 keeps the
+        // thread-per-sequence kernel (A/B knob)
+        const char* legacy = getenv("OCO_FILL_LEGACY");
+        if (fill_warp_eligible(family, d) && T <= 0x7fffffff && !(legacy && legacy[0] == '1'))
+            return launch_fill_warp(key_a, key_c0, keys, B, T, d, out_f32, z, y, st);
+    }
     FillArgs a;
     a.key_a = key_a; a.key_c0 = key_c0; a.keys = keys; a.T = T; a.B = B; a.family = family; a.p_flip = p_flip;
     a.block_len = block_len; a.z = z; a.y = y;

@@ -70,6 +70,11 @@ cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, in
 cudaError_t launch_fill(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t B, int64_t T, int d,
                         double p_flip, int64_t block_len, int out_f32, void* z, void* y, cudaStream_t st);
 
+// warp-per-sequence generator for the g-path family, any d <= 128 (kernels_fill_warp.cu)
+bool fill_warp_eligible(int family, int d);
+cudaError_t launch_fill_warp(uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t B, int64_t T, int d, int out_f32,
+                             void* z, void* y, cudaStream_t st);
+
 // Streamed simulators on device-resident sequences (z[B][T][d], y[B][T]; f32 or f64).
 cudaError_t launch_sim_stream(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                               const Variants& v, const double* scale_tab, const double* comparator,

@@ -56,8 +56,10 @@ def test_rcp_inrange_matches_division(eng):
         assert int(out.view(np.uint64)[0]) == 0
 
 
-@pytest.mark.parametrize("d", [1, 2, 5, 8, 64])
+@pytest.mark.parametrize("d", [1, 2, 5, 7, 8, 13, 64, 100, 128])
 def test_gen_gpath_bit_exact(eng, d):
+    """Warp-per-sequence generator (jump-ahead PCG64, role walk over the failing draws, numpy's pairwise row norm):
+    rows and labels equal the oracle's bit for bit for any d <= 128; the round-1 thread-per-sequence kernel agrees."""
     T = 257 if d < 64 else 96
     z, y = eng.gen_sequences("gpath", 5, T, d, key_a=3, key_c0=7)
     for b in range(5):
@@ -65,6 +67,24 @@ def test_gen_gpath_bit_exact(eng, d):
         assert (bits(z[b]) == bits(zo)).all() and (y[b] == yo).all()
     z32, y32 = eng.gen_sequences("gpath", 2, T, d, key_a=3, key_c0=7, dtype=np.float32)
     assert (z32[1] == O.gen_gpath(3, T, 8, d)[0].astype(np.float32)).all()
+    if d in (1, 5, 64):                                           # legacy kernel (OCO_FILL_LEGACY=1) on the shapes it supports
+        import os
+        os.environ["OCO_FILL_LEGACY"] = "1"
+        try:
+            zl, yl = eng.gen_sequences("gpath", 5, T, d, key_a=3, key_c0=7)
+        finally:
+            del os.environ["OCO_FILL_LEGACY"]
+        assert (bits(zl) == bits(z)).all() and (yl == y).all()
+
+
+def test_gen_gpath_long_sequences_and_ragged_tails(eng):
+    """Long streams (tail draws, carried wedge / tail candidates across 32-raw rounds) and the lane-0 finish of the
+    last < 34 normals: T*d not a multiple of anything, T = 1, T*d < 34."""
+    for d, T, B in ((64, 2000, 2), (5, 10_000, 2), (9, 3001, 2), (3, 1, 2), (2, 2, 1), (33, 1, 1), (1, 35, 3), (128, 517, 1)):
+        z, y = eng.gen_sequences("gpath", B, T, d, key_a=11, key_c0=5)
+        for b in range(B):
+            zo, yo = O.gen_gpath(11, T, 5 + b, d)
+            assert (bits(z[b]) == bits(zo)).all() and (y[b] == yo).all(), (d, T, b)
 
 
 def test_gen_case_families_bit_exact(eng):

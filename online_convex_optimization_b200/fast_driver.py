@@ -147,8 +147,28 @@ def run_experiment(cfg: ExperimentConfig = None) -> dict:
     return {"T_grid": [int(t) for t in cfg.T_grid], "g_emp": g_emp, "stats_by_case": stats_by_case}
 
 
-def main(out_path: str = "fast_driver_b200.json") -> None:
+def plot_empirical_g(T_grid, g_emp, *, out_path: str = "empirical_g_T_fast.png") -> None:
+    """fast_driver.py:140-158 (needs matplotlib; see plotting.py)."""
+    from . import plotting
+    plotting.plot_empirical_g(T_grid, g_emp, out_path=out_path)
+
+
+def plot_comparisons(T_grid, stats_by_case, *, out_path: str = "algorithm_comparison_fast.png") -> None:
+    """fast_driver.py:161-194 (needs matplotlib; see plotting.py)."""
+    from . import plotting
+    plotting.plot_comparisons(T_grid, stats_by_case, out_path=out_path, runs_by_title=RUNS_BY_TITLE, reps_by_title=REPLICATES_BY_TITLE)
+
+
+def main(out_path: str = "fast_driver_b200.json", *, plots: bool = True) -> None:
+    """fast_driver.main (fast_driver.py:201-220): the experiment, its JSON, and -- when matplotlib is importable --
+    the reference's two figures under the reference's file names."""
     res = run_experiment()
+    if plots:
+        try:
+            plot_empirical_g(res["T_grid"], res["g_emp"], out_path="empirical_g_T_fast.png")
+            plot_comparisons(res["T_grid"], res["stats_by_case"], out_path="algorithm_comparison_fast.png")
+        except ImportError as e:
+            print("figures skipped:", e)
     ser = {"T_grid": res["T_grid"], "g_emp": {str(k): v for k, v in res["g_emp"].items()},
            "stats_by_case": {t: {k: {"mean": m.tolist(), "ci": c.tolist()} for k, (m, c) in st.items()}
                              for t, st in res["stats_by_case"].items()}}

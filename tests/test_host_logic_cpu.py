@@ -75,3 +75,45 @@ def test_exact_solver_buffer_protocol_without_device():
     assert (s._solve_current() == 0).all()              # empty prefix -> zero action, no solve
     with pytest.raises(ValueError):
         ex.replay_exact_ftl(z, y, np.zeros((3, 2)))     # actions must be (T+1, d) (exact_ftl.py:314-315)
+
+
+def test_plotting_shim_draws_the_reference_figures(tmp_path, monkeypatch):
+    """plotting.py with a stand-in matplotlib: g(T) figure = 3 curves, comparison figure = one panel per case with
+    one line per algorithm and a CI band only where the CI is non-zero; without matplotlib a clear ImportError."""
+    import sys
+    import types
+    from unittest.mock import MagicMock
+    import numpy as np
+    from online_convex_optimization_b200 import plotting
+    fake = types.ModuleType("matplotlib"); fake.use = lambda *a, **k: None
+    plt = MagicMock()
+    axes_made = []
+
+    def subplots(*a, **k):
+        fig = MagicMock()
+        if a and len(a) >= 2:
+            arr = np.empty((a[0], a[1]), dtype=object)
+            for i in range(a[0]):
+                for j in range(a[1]):
+                    ax = MagicMock(); ax.plot.return_value = (MagicMock(),); arr[i, j] = ax; axes_made.append(ax)
+            return fig, arr
+        ax = MagicMock(); ax.plot.return_value = (MagicMock(),); axes_made.append(ax)
+        return fig, ax
+    plt.subplots.side_effect = subplots
+    fake.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", fake)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    Tg = np.array([100, 200, 300])
+    plotting.plot_empirical_g(Tg, {100: 6.0, 200: 8.3, 300: 10.4}, out_path=str(tmp_path / "g.png"))
+    assert axes_made[-1].plot.call_count == 3
+    stats = {"A": {"FTRL": (np.ones(3), np.zeros(3)), "FTL": (np.ones(3), np.full(3, 0.1))},
+             "B": {"FTRL": (np.ones(3), np.zeros(3))}, "C": {"FTRL": (np.ones(3), np.zeros(3))}}
+    n0 = len(axes_made)
+    plotting.plot_comparisons(Tg, stats, out_path=str(tmp_path / "c.png"))
+    panels = axes_made[n0:]
+    assert len(panels) == 4 and panels[0].plot.call_count == 2 and panels[0].fill_between.call_count == 1
+    assert panels[3].axis.call_count == 1                      # unused fourth panel switched off
+    monkeypatch.setitem(sys.modules, "matplotlib", None)
+    import pytest
+    with pytest.raises(ImportError):
+        plotting.plot_empirical_g(Tg, {100: 6.0, 200: 8.3, 300: 10.4})

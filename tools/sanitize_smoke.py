@@ -19,4 +19,15 @@ zw, yw = engine.gen_sequences("gpath", 9, 42, 64)
 w = engine.simulate_batch(zw, yw, [0, 1], [R2, R2], comparator="linear"); w = engine.simulate_batch(zw, yw, [0], [R2])
 zw, yw = engine.gen_sequences("iid", 3, 20, 5, key_a=2025, key_c0=13); zf, yf = engine.gen_sequences("flip", 2, 9, 5)
 g, st = engine.g_sweep([10, 20], runs=33)
+# round 2 kernels: pipelined sweep (d = 1 exact, d = 3 / 5 single-pass comparator, several rounds per CTA), warp-cooperative
+# generator at an odd d, wide-d exact FTL / replay / fixed comparator, staged float32 kernel
+r = engine.regret_sweep("gpath", 700, 33, 3, [0, 1, 0], [R2, R2, 0.2], comparator="linear", full=True)
+r = engine.regret_sweep("gpath", 128 * 148 * 5 + 5, 6, 5, [0], [R2], comparator="linear")
+g, st = engine.g_sweep([10, 21], runs=33, comparator="linear")
+zo, yo = engine.gen_sequences("gpath", 5, 37, 13); zo, yo = engine.gen_sequences("gpath", 3, 9, 128, dtype=np.float32)
+z10, y10 = engine.gen_sequences("gpath", 6, 40, 10)
+e10 = engine.exact_ftl_prefix_batch(z10, y10); rp = engine.replay_actions(z10, y10, e10["actions"])
+a10 = engine.simulate_batch(z10, y10, [0, 1], [R2, R2], full=True, comparator_action=e10["actions"][:, -1, :])
+zf, yf = engine.gen_sequences("gpath", 70, 48, 5, dtype=np.float32)
+a32 = engine.simulate_batch(zf, yf, [0, 1, 0, 0, 1], [R2, R2, 0.1, 3.0, 1.0], compute="f32", full=True)
 print("sanitize smoke done", float(r["stats"][0, 0]), float(w[0, 0]))

@@ -21,7 +21,12 @@ from ._lib import (COMPARATOR_LINEAR, COMPARATOR_TWO_PASS, FAM_FLIP, FAM_GPATH, 
 
 SQRT2 = math.sqrt(2.0)
 FAMILIES = {"gpath": FAM_GPATH, "iid": FAM_IID, "noisy": FAM_NOISY, "flip": FAM_FLIP, "switch": FAM_SWITCH}
-COMPARATORS = {"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR}
+class _Comparators(dict):
+    def __missing__(self, key):
+        raise ValueError(f"comparator must be 'two_pass' or 'linear' (got {key!r})")
+
+
+COMPARATORS = _Comparators({"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR})
 
 
 def _vp(a) -> C.c_void_p:

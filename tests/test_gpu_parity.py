@@ -528,3 +528,46 @@ def test_float32_mode_small_d_knife_edges(eng):
             assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (rec["spec"], key, got, want)
             n += 1
     assert n == 24
+
+
+def test_round2_paths_edge_cases(eng):
+    """Empty / degenerate shapes through the round-2 kernels: T = 0, B = 0, B = 1, explicit keys, d at the limits."""
+    for d in (1, 3, 5):
+        for mode in ("two_pass", "linear"):
+            r = eng.regret_sweep("gpath", 3, 0, d, [0, 1], [R2, R2], comparator=mode, full=True)
+            assert (r["regret"] == 0).all() and (r["cum_loss"] == 0).all() and (r["comp_loss"] == 0).all()
+            r = eng.regret_sweep("gpath", 0, 10, d, [0], [R2], comparator=mode)
+            assert r["regret"].shape == (0, 1) and (r["stats"] == 0).all()
+    keys = np.array([[7, 11 + b] for b in range(5)], dtype=np.uint64)      # explicit (a, c) keys == implicit key_a / key_c0 + b
+    a = eng.regret_sweep("gpath", 5, 77, 4, [0, 1], [R2, 0.5], key_a=7, key_c0=11, comparator="linear")["regret"]
+    b = eng.regret_sweep("gpath", 5, 77, 4, [0, 1], [R2, 0.5], keys=keys, comparator="linear")["regret"]
+    assert (bits(a) == bits(b)).all()
+    g, st = eng.g_sweep(np.array([], dtype=np.int64), runs=5, comparator="linear")
+    assert g.shape == (0,)
+    g, st = eng.g_sweep(np.array([50]), runs=0, comparator="linear")
+    assert g[0] == 0.0
+    z, y = eng.gen_sequences("gpath", 0, 10, 7)
+    assert z.shape == (0, 10, 7)
+    z, y = eng.gen_sequences("gpath", 2, 0, 7)
+    assert z.shape == (2, 0, 7)
+    with pytest.raises(ValueError):
+        eng.gen_sequences("gpath", 1, 4, 129)
+    with pytest.raises(ValueError):
+        eng.regret_sweep("gpath", 1, 4, 2, [0], [R2], comparator="nonsense")
+    # wide-d exact paths at the limits
+    for d in (9, 256):
+        zz, yy = O.gen_gpath(2, 30, 0, d) if d <= 128 else (None, None)
+        if zz is None:
+            rng = np.random.default_rng(1)
+            zz = rng.standard_normal((30, d)); zz /= np.maximum(1.0, np.linalg.norm(zz, axis=1, keepdims=True)); yy = np.sign(rng.standard_normal(30))
+        ex = eng.exact_ftl_prefix_batch(zz[None], yy[None])
+        assert int(ex["status"][0]) == 0
+        v = np.cumsum(yy[:, None] * zz, axis=0)
+        want = v / np.linalg.norm(v, axis=1, keepdims=True)
+        assert np.allclose(ex["actions"][0, 1:], want, rtol=1e-12, atol=1e-14)
+        rp = eng.replay_actions(zz[None], yy[None], ex["actions"])
+        assert abs(rp["regret"][0] - ex["regret"][0]) <= REL * max(1.0, abs(ex["cum_loss"][0]))
+    ex = eng.exact_ftl_prefix_batch(np.zeros((2, 0, 12)), np.zeros((2, 0)))
+    assert ex["actions"].shape == (2, 1, 12) and (ex["regret"] == 0).all()
+    with pytest.raises(ValueError):
+        eng.exact_ftl_prefix_batch(np.zeros((1, 3, 257)), np.ones((1, 3)))

@@ -396,49 +396,45 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                         const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
                         if (fabs(df) > 0.0) th2l[0] = th2l[0] + gz;         // zero / NaN diff: no step (fast_algorithms.py:27-34)
                     }
-                    // the NF FTRL variants are independent chains: all actions first, then the projections, voted per HALF
-                    // (variants are usually passed in eta0 order: the small-eta half almost never projects, the large-eta half
-                    // almost always), branch-free reciprocals the scheduler can interleave, then all the steps
-                    double x1[NF], n2v[NF];
+                    // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
+                    // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
+                    // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
+                    // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
                     constexpr int H = NF >= 4 ? NF / 2 : NF;
-                    int top0 = 0, top1 = 0;                         // max over the half of the high word of n2 (n2 >= 0 or NaN)
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) {
-                        x1[k] = scn[k] * th2r[k][0];
-                        n2v[k] = x1[k] * x1[k];
-                        if (k < H) top0 = max(top0, __double2hiint(n2v[k])); else top1 = max(top1, __double2hiint(n2v[k]));
-                    }
-                    auto project_range = [&](int lo, int hi, int top) {
+                    for (int h0 = 0; h0 < NF; h0 += H) {
+                        double x1[H], n2v[H];
+                        int top = 0;                                // max over the half of the high word of n2 (n2 >= 0 or NaN)
+#pragma unroll
+                        for (int k = 0; k < H; ++k) {
+                            x1[k] = scn[h0 + k] * th2r[h0 + k][0];
+                            n2v[k] = x1[k] * x1[k];
+                            top = max(top, __double2hiint(n2v[k]));
+                        }
                         if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
                             if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
 #pragma unroll
-                                for (int k = 0; k < NF; ++k) {
-                                    if (k >= lo && k < hi) {
-                                        double xx[1] = {x1[k]};
-                                        project_unit_ball<1>(xx, n2v[k], mask);
-                                        x1[k] = xx[0];
-                                    }
+                                for (int k = 0; k < H; ++k) {
+                                    double xx[1] = {x1[k]};
+                                    project_unit_ball<1>(xx, n2v[k], mask);
+                                    x1[k] = xx[0];
                                 }
                             } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
 #pragma unroll
-                                for (int k = 0; k < NF; ++k) {
-                                    if (k >= lo && k < hi) {
-                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
-                                        if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
-                                    }
+                                for (int k = 0; k < H; ++k) {
+                                    const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
+                                    if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
                                 }
                             }
                         }
-                    };
-                    project_range(0, H, top0);
-                    if (H < NF) project_range(H, NF, top1);
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) {
-                        const double df = z0 * x1[k] - y;
-                        Sr[k] = Sr[k] + fabs(df);
-                        const int sgn = __double2hiint(df) & 0x80000000;
-                        const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
-                        if (fabs(df) > 0.0) th2r[k][0] = th2r[k][0] + gz;
+                        for (int k = 0; k < H; ++k) {
+                            const double df = z0 * x1[k] - y;
+                            Sr[h0 + k] = Sr[h0 + k] + fabs(df);
+                            const int sgn = __double2hiint(df) & 0x80000000;
+                            const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
+                            if (fabs(df) > 0.0) th2r[h0 + k][0] = th2r[h0 + k][0] + gz;
+                        }
                     }
                 } else {
                 const int yhi = __double2hiint(y);

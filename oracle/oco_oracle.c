@@ -26,7 +26,7 @@
  * (256-layer ziggurat), Generator.random, Generator.choice, np.linalg.norm /
  * add.reduce pairwise summation, glibc 2.39 log1p (FMA ifunc variant).  They
  * are restated here from their published algorithms and pinned bit-exactly
- * against numpy in tests/test_oracle_rng.py and against golden vectors generated
+ * against numpy in tests/test_oracle_golden.py and against golden vectors generated
  * by running the reference itself (tests/golden/, tools/make_golden.py).
  *
  * Numerics: build with  -O2 -ffp-contract=off -fno-fast-math  (see Makefile).
@@ -137,7 +137,7 @@ static inline double pcg64_double(pcg64_t *g) {
  * dispatches to __log1p_fma (sysdeps/ieee754/dbl-64/s_log1p.c built with
  * -mfma).  The fused operations below were read off the disassembly of
  * libm.so.6 in this image; checked bit-exact against np.log1p in
- * tests/test_oracle_rng.py. */
+ * tests/test_oracle_golden.py. */
 static double log1p_glibc_fma(double x) {
     static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
         Lp1 = 6.666666666666735130e-01, Lp2 = 3.999999999940941908e-01, Lp3 = 2.857142874366239149e-01,

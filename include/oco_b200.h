@@ -174,7 +174,8 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
                           double* regret, double* cum_loss, double* comp_loss, double* stats, int device);
 
 /* Same with an explicit comparator_mode (the entry points above are OCO_COMPARATOR_TWO_PASS, bit-exact for d <= 5):
- * OCO_COMPARATOR_LINEAR applies to the g-path family with 2 <= d <= 5 (other shapes ignore it and stay exact):
+ * OCO_COMPARATOR_LINEAR applies to the g-path family with 2 <= d <= 8 (d = 6, 7, 8 exist in this mode only; other
+ * shapes ignore it and stay exact):
  * rows are regenerated in registers instead of being parked in a scratch slab (no DRAM traffic) and the
  * comparator loss of fast_algorithms.py:113-114 is T/2 - ||theta_T|| -- valid because the kernel verifies
  * sign(q_t - y_t) == -y_t on every step; a sequence that ever violates it takes the literal second pass.

@@ -87,11 +87,12 @@ int upload_keys(const uint64_t* keys, int64_t B, DevBuf& buf, cudaStream_t st, c
     return OCO_OK;
 }
 
-int check_family(int family, int d, bool fused) {
+int check_family(int family, int d, bool fused, int comparator_mode = OCO_COMPARATOR_TWO_PASS) {
     if (family < OCO_FAM_GPATH || family > OCO_FAM_SWITCH) return fail(OCO_ERR_VALUE, "unknown sequence family %d", family);
     if (fused) {
         if (family > OCO_FAM_NOISY) return fail(OCO_ERR_VALUE, "fused sweep supports the seeded families only (got %d)", family);
-        if (d > 5) return fail(OCO_ERR_VALUE, "fused sweep supports d <= 5 (got %d); generate + simulate instead", d);
+        const int dmax = (family == OCO_FAM_GPATH && comparator_mode == OCO_COMPARATOR_LINEAR) ? 8 : 5;   // gsweep_kernel: d <= 8
+        if (d > dmax) return fail(OCO_ERR_VALUE, "fused sweep supports d <= %d here (got %d; g-path with OCO_COMPARATOR_LINEAR: d <= 8); generate + simulate instead", dmax, d);
     } else if (family == OCO_FAM_GPATH) {
         if (d > 128) return fail(OCO_ERR_VALUE, "g-path generator supports d <= 128 (got %d)", d);
     } else if (family <= OCO_FAM_NOISY) {
@@ -493,7 +494,7 @@ OCO_API int oco_regret_sweep_mode(int family, uint64_t key_a, uint64_t key_c0, c
         return fail(OCO_ERR_VALUE, "comparator_mode must be OCO_COMPARATOR_TWO_PASS or OCO_COMPARATOR_LINEAR");
     if (B < 0 || T < 0 || d < 1) return fail(OCO_ERR_VALUE, "need B >= 0, T >= 0, d >= 1");
     if (A < 1 || A > OCO_MAX_VARIANTS) return fail(OCO_ERR_VALUE, "need 1 <= A <= %d (got %d)", OCO_MAX_VARIANTS, A);
-    if (int rc = check_family(family, d, true)) return rc;
+    if (int rc = check_family(family, d, true, comparator_mode)) return rc;
     Variants v; Etas e;
     if (int rc = make_variants(alg_flag, eta0, A, v, e)) return rc;
     cudaStream_t st = (cudaStream_t)stream;

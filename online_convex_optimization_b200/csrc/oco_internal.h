@@ -60,6 +60,7 @@ cudaError_t launch_sweep_gpath(const struct SweepArgs& a, int d, cudaStream_t st
 // g-path, 2 <= d <= 5, single-pass comparator, rows regenerated instead of parked in HBM (gsweep_impl.cuh)
 cudaError_t launch_gsweep_lo(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 1, 2, 3
 cudaError_t launch_gsweep_hi(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 4, 5
+cudaError_t launch_gsweep_wide(const struct SweepArgs& a, int d, cudaStream_t st); // d = 6, 7, 8
 cudaError_t launch_sweep_iid(const struct SweepArgs& a, int d, cudaStream_t st);
 int sweep_gpath_blocks(int64_t n_runs);
 // stats[a*4 + {0,1,2,3}] = max, sum, sumsq, count over all runs (fixed reduction order)

@@ -282,7 +282,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #endif
 
 template <int D, int NFTL, int NF>
-__global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : OCO_GSWEEP_MIN_BLOCKS_NF)) gsweep_kernel(const SweepArgs p) {
+__global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : OCO_GSWEEP_MIN_BLOCKS_NF) * kSweepBlockScale) gsweep_kernel(const SweepArgs p) {
     static_assert(D >= 1 && D <= 8, "thread-per-sequence kernel: theta lives in registers");
     __shared__ ZigTab2 tb;
     __shared__ double red[kSweepBlock / 32][3];

@@ -37,7 +37,11 @@
 
 namespace oco {
 
-constexpr int kSweepBlock = 128;
+#ifndef OCO_SWEEP_BLOCK
+#define OCO_SWEEP_BLOCK 128
+#endif
+constexpr int kSweepBlock = OCO_SWEEP_BLOCK;          // sequences (threads) per CTA and per work item
+constexpr int kSweepBlockScale = 128 / kSweepBlock;   // resident-CTA targets below are stated for 128-thread CTAs
 #ifndef OCO_SWEEP_ROW_AHEAD
 #define OCO_SWEEP_ROW_AHEAD 3
 #endif
@@ -66,7 +70,7 @@ struct SweepArgs {
 #define OCO_SWEEP_MIN_BLOCKS 5
 #endif
 template <class Stream, int D, int NFTL, int NF>
-__global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 4)) sweep_kernel(const SweepArgs p) {
+__global__ void __launch_bounds__(kSweepBlock, (D <= 2 ? OCO_SWEEP_MIN_BLOCKS : 4) * kSweepBlockScale) sweep_kernel(const SweepArgs p) {
     __shared__ ZigTables tb;
     __shared__ double red[kSweepBlock / 32][3];
     zig_tables_load(tb);

@@ -291,14 +291,23 @@ def smart_batch_device(z, y, theta_threshs, eta0s, *, mode: str = "exact"):
 
 
 def gen_sequences_device(family, B: int, T: int, d: int = 5, *, key_a: int = 0, key_c0: int = 0, keys=None,
-                         p_flip: float = -1.0, block_len: int = 20, dtype=None, device=None):
+                         p_flip: float = -1.0, block_len: int = 20, dtype=None, device=None, out=None):
+    """Sequences of one family written to device memory (enqueued on the current stream, not synchronised).
+    out=(z, y): existing contiguous CUDA tensors of shape (B,T,d) / (B,T) to fill (double-buffered pipelines)."""
     torch = _torch()
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
-    if dtype is None:
-        dtype = torch.float64 if fam == FAM_GPATH else torch.float32
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    z = torch.empty((B, T, d), dtype=dtype, device=dev)
-    y = torch.empty((B, T), dtype=dtype, device=dev)
+    if out is not None:
+        z, y = out
+        if tuple(z.shape) != (B, T, d):
+            raise ValueError(f"out[0] must have shape ({B}, {T}, {d})")
+        _check_device_inputs(torch, z, y)
+        dtype, dev = z.dtype, z.device
+    else:
+        if dtype is None:
+            dtype = torch.float64 if fam == FAM_GPATH else torch.float32
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        z = torch.empty((B, T, d), dtype=dtype, device=dev)
+        y = torch.empty((B, T), dtype=dtype, device=dev)
     k = _keys(keys, B)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().oco_gen_sequences(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), block_len,

@@ -470,9 +470,14 @@ def run_other_single_gpu(args, torch, engine, local, fp64_peak):
         zd, yd = engine.gen_sequences_device("gpath", B, T, 5, dtype=torch.float64)
         th, et = [math.sqrt(2 * T), 60.0], [R2, R2]
         ms, _ = timed(torch, lambda: engine.smart_batch_device(zd, yd, th, et, mode="linear"), 2)
-        ms2, _ = timed(torch, lambda: engine.smart_batch_device(zd[:592], yd[:592], th, et, mode="exact"), 1)
+        ms2, (_, sw2) = timed(torch, lambda: engine.smart_batch_device(zd, yd, th, et, mode="exact"), 2)
+        ms3, _ = timed(torch, lambda: engine.smart_batch_device(zd[:592], yd[:592], th, et, mode="exact"), 2)
         ex["smart_t1e4"] = {"linear_mode": {"value": B * T * 2 / (ms * 1e-3), "sequences": B, "ms": ms},
-                            "exact_mode": {"value": 592 * T * 2 / (ms2 * 1e-3), "sequences": 592, "ms": ms2},
+                            "exact_mode": {"value": B * T * 2 / (ms2 * 1e-3), "sequences": B, "ms": ms2,
+                                           "switched_fraction": float((sw2 >= 0).double().mean().item()),
+                                           "note": "literal switch test; the O(t) prefix loss is evaluated only in rounds the exact bound "
+                                                   "0.5((t+1) - s.vy) <= s_loss cannot rule out (kernels_warp.cu: smart_prune_margin)"},
+                            "exact_mode_592_sequences_cta_kernel": {"value": 592 * T * 2 / (ms3 * 1e-3), "ms": ms3},
                             "unit": "trajectory-steps/s", "T": T, "d": 5, "thresholds": 2}
         del zd, yd
     except Exception as e:

@@ -204,6 +204,19 @@ struct SmartArgs {
     int* flags;                           // linear kernel: [B] set to 1 when a row violates the precondition
 };
 
+// EXACT pruning of the O(t) prefix loss (both exact kernels).  For labels y_i = +-1, |q - y| >= 1 - y q for ANY q, so
+//   s_loss = sum_{i<=t} 0.5|z_i.s - y_i|  >=  0.5((t + 1) - s.vy),   vy = sum_{i<=t} y_i z_i        (O(d) per round)
+// and the switch test `ftl_loss - s_loss >= thresh` (fast_algorithms.py:157-160) cannot fire while
+// ftl_loss - 0.5((t + 1) - s.vy) < min(unswitched thresholds) - delta.  delta = 1e-9 (t+1) + 2.3e-16 (t+1)^2 covers the
+// worst-case rounding of every sum involved (the reference's own sequential s_loss included), so a skipped round is a
+// round the reference does not switch in; otherwise the literal prefix loss is evaluated and decides, as before.
+// Sequences that never come near their threshold (every iid stream of the reference's drivers) cost O(T d) instead of
+// O(T^2 d) with unchanged results; no assumption on the row norms (unlike smart_linear_kernel).
+__device__ __forceinline__ double smart_prune_margin(int64_t t) {
+    const double n = (double)(t + 1);
+    return 1e-9 * n + 2.3e-16 * n * n;
+}
+
 // CACHED: the warp first copies its sequence, widened to double, into shared memory as D + 1 planes
 // [j][i] (conflict-free for lane-strided rows); the O(t) prefix loss of every round then reads LDS.64
 // instead of re-fetching and re-converting the rows from L1 / L2 (35 % of the stall samples and, for
@@ -250,12 +263,19 @@ __global__ void __launch_bounds__(kSmartWarps * 32) smart_kernel(const SmartArgs
     }
     double ftl_loss = 0.0;
     int n_unswitched = A;
+    double vy[D];                        // sum y_i z_i (pruning bound)
+    bool pm1 = true;                     // every label so far is +-1
+#pragma unroll
+    for (int j = 0; j < D; ++j) vy[j] = 0.0;
 
     for (int64_t t = 0; t < p.T; ++t) {
         double z[D], hz[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) { z[j] = zval(t, j); hz[j] = 0.5 * z[j]; }
         const double y = yval(t);
+        pm1 = pm1 && (y == 1.0 || y == -1.0);
+#pragma unroll
+        for (int j = 0; j < D; ++j) vy[j] = vy[j] + y * z[j];
         double x[D];
         action_ftl<D>(thl, x);
         const double pf = dot_seq<D>(z, x);
@@ -290,9 +310,19 @@ __global__ void __launch_bounds__(kSmartWarps * 32) smart_kernel(const SmartArgs
                 }
             }
         }
-        if (n_unswitched > 0) {
-            double s[D];
+        bool need = n_unswitched > 0;
+        double s[D];
+        if (need) {
             action_ftl<D>(thl, s);
+            if (pm1) {                                           // exact pruning (see smart_prune_margin)
+                double thmin = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+                for (int a = 0; a < kSmartMaxA; ++a) if (a < A && sw[a] < 0) thmin = fmin(thmin, thresh[a]);
+                const double lin = 0.5 * ((double)(t + 1) - dot_seq<D>(s, vy));
+                if (ftl_loss - lin < thmin - smart_prune_margin(t)) need = false;
+            }
+        }
+        if (need) {
             double part = 0.0;
 #pragma unroll 4
             for (int64_t i = lane; i <= t; i += 32) {
@@ -393,6 +423,10 @@ __global__ void __launch_bounds__(kSmartCtaThreads) smart_cta_kernel(const Smart
     }
     double ftl_loss = 0.0;
     int n_unswitched = A;
+    double vy[D];                        // sum y_i z_i (pruning bound, warp 0)
+    bool pm1 = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) vy[j] = 0.0;
 
     for (int64_t t = 0; t < T; ++t) {
         if (wib == 0) {                                               // fast_algorithms.py:133-156, as in smart_kernel
@@ -400,6 +434,9 @@ __global__ void __launch_bounds__(kSmartCtaThreads) smart_cta_kernel(const Smart
 #pragma unroll
             for (int j = 0; j < D; ++j) { z[j] = zval(t, j); hz[j] = 0.5 * z[j]; }
             const double y = yval(t);
+            pm1 = pm1 && (y == 1.0 || y == -1.0);
+#pragma unroll
+            for (int j = 0; j < D; ++j) vy[j] = vy[j] + y * z[j];
             double x[D];
             action_ftl<D>(thl, x);
             const double dff = dot_seq<D>(z, x) - y;
@@ -432,17 +469,25 @@ __global__ void __launch_bounds__(kSmartCtaThreads) smart_cta_kernel(const Smart
                     }
                 }
             }
-            if (n_unswitched > 0) {
+            bool need_w = n_unswitched > 0;
+            if (need_w) {
                 double s[D];
                 action_ftl<D>(thl, s);
-                if (lane < D) {
+                if (pm1) {                                        // exact pruning (see smart_prune_margin)
+                    double thmin = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+                    for (int a = 0; a < kSmartMaxA; ++a) if (a < A && sw[a] < 0) thmin = fmin(thmin, thresh[a]);
+                    const double lin = 0.5 * ((double)(t + 1) - dot_seq<D>(s, vy));
+                    if (ftl_loss - lin < thmin - smart_prune_margin(t)) need_w = false;
+                }
+                if (need_w && lane < D) {
                     double out = 0.0;
 #pragma unroll
                     for (int j = 0; j < D; ++j) if (j == lane) out = s[j];
                     sh_s[lane] = out;
                 }
             }
-            if (lane == 0) sh_need = n_unswitched > 0 ? 1 : 0;
+            if (lane == 0) sh_need = need_w ? 1 : 0;
         }
         __syncthreads();
         const bool need = sh_need != 0;                               // uniform across the CTA

@@ -6,7 +6,7 @@ T, B = 10000, 4096
 z, y = engine.gen_sequences_device("gpath", B, T, 5, dtype=torch.float64)
 th, et = [math.sqrt(2 * T), 60.0], [math.sqrt(2)] * 2
 for mode in ("linear", "exact"):
-    nb = B if mode == "linear" else 512
+    nb = B
     r, sw = engine.smart_batch_device(z[:nb], y[:nb], th, et, mode=mode); torch.cuda.synchronize()
     t0 = time.perf_counter(); r, sw = engine.smart_batch_device(z[:nb], y[:nb], th, et, mode=mode); torch.cuda.synchronize()
     dt = time.perf_counter() - t0

@@ -68,6 +68,12 @@ extern "C" {
  *     row; sequences that violate it fall back to the second pass).  Tolerance 1e-12 relative. */
 #define OCO_COMPARATOR_TWO_PASS 0
 #define OCO_COMPARATOR_LINEAR 1
+/* oco_g_sweep_mode_host only: the EXACT maximum at single-pass speed.  For labels +-1, |q - y| >= 1 - y q, so the
+ * single-pass regret (OCO_COMPARATOR_LINEAR) is an upper bound of the literal one for every run; only the runs whose
+ * bound reaches the largest bound (minus a margin covering worst-case rounding) can attain the maximum, and only
+ * those -- typically one run -- take the literal fast_algorithms.py:113-114 second pass.  g_max is the reference's
+ * value bit for bit; the sum / sum of squares in `stats` are the single-pass ones (1e-12 class). */
+#define OCO_COMPARATOR_EXACT_MAX 2
 
 OCO_API const char* oco_last_error(void);
 OCO_API int oco_abi_version(void);

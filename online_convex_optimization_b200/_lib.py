@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboco_b200.so")
 OCO_OK, OCO_ERR_VALUE, OCO_ERR_RUNTIME = 0, 1, 2
 OCO_F32, OCO_F64 = 0, 1
 FAM_GPATH, FAM_IID, FAM_NOISY, FAM_FLIP, FAM_SWITCH = 0, 1, 2, 3, 4
-COMPARATOR_TWO_PASS, COMPARATOR_LINEAR = 0, 1
+COMPARATOR_TWO_PASS, COMPARATOR_LINEAR, COMPARATOR_EXACT_MAX = 0, 1, 2
 MAX_VARIANTS, MAX_SMART_THRESHOLDS = 64, 4
 
 _vp, _i, _i64, _u64, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double

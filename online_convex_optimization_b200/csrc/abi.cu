@@ -568,10 +568,56 @@ OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int
     return oco_g_sweep_mode_host(T_grid, nT, run_lo, n_runs, base_seed, d, eta0, g_max, stats, OCO_COMPARATOR_TWO_PASS, device);
 }
 
+// Exact maximum of one horizon at single-pass speed (OCO_COMPARATOR_EXACT_MAX, see the header): single-pass sweep with
+// per-run regrets, candidate selection on the device, literal two-pass simulation of the candidates' sequences.
+// Writes (max, sum, sumsq, count) to stats_dev[0..3] (device); returns OCO_OK or an error code.
+static int g_sweep_exact_max_one(int64_t T, uint64_t run_lo, int64_t n_runs, uint64_t base_seed, int d, double eta0,
+                                 double* stats_dev, cudaStream_t st) {
+    const int flag = OCO_ALG_FTRL;
+    constexpr int kCap = 4096;
+    DevBuf reg, idx, cnt;
+    CU(reg.alloc(sizeof(double) * (size_t)n_runs, st));
+    CU(idx.alloc(sizeof(int64_t) * kCap, st));
+    CU(cnt.alloc(sizeof(int), st));
+    if (int rc = oco_regret_sweep_mode(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T, d, -1.0, &flag, &eta0, 1,
+                                       reg.as<double>(), nullptr, nullptr, stats_dev, OCO_COMPARATOR_LINEAR, st)) return rc;
+    const double Td = (double)T, margin = 1e-9 * Td + 2.3e-16 * Td * Td;    // worst-case rounding of every sum involved
+    CU(launch_select_candidates(reg.as<double>(), n_runs, 1, stats_dev, margin, idx.as<int64_t>(), cnt.as<int>(), kCap, st));
+    int n_cand = 0;
+    std::vector<int64_t> hidx(kCap);
+    CU(cudaMemcpyAsync(&n_cand, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hidx.data(), idx.p, sizeof(int64_t) * kCap, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_cand > kCap) {       // a pathological pile-up at the maximum: the literal pass over every run
+        return oco_regret_sweep_mode(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T, d, -1.0, &flag, &eta0, 1,
+                                     nullptr, nullptr, nullptr, stats_dev, OCO_COMPARATOR_TWO_PASS, st);
+    }
+    // literal two-pass regrets of the candidates: generate their sequences (explicit keys) and simulate (bit-exact for d <= 8)
+    std::vector<uint64_t> keys(2 * (size_t)n_cand);
+    for (int k = 0; k < n_cand; ++k) { keys[2 * k] = base_seed; keys[2 * k + 1] = run_lo + (uint64_t)hidx[k]; }
+    DevBuf zc, yc, rc_, mx;
+    CU(zc.alloc(sizeof(double) * (size_t)n_cand * T * d, st));
+    CU(yc.alloc(sizeof(double) * (size_t)n_cand * T, st));
+    CU(rc_.alloc(sizeof(double) * (size_t)n_cand, st));
+    if (int rc = oco_gen_sequences(OCO_FAM_GPATH, 0, 0, keys.data(), n_cand, T, d, -1.0, 20, OCO_F64, zc.p, yc.p, st)) return rc;
+    if (int rc = oco_simulate_batch(zc.p, yc.p, OCO_F64, OCO_F64, n_cand, T, d, &flag, &eta0, 1, nullptr, rc_.as<double>(),
+                                    nullptr, nullptr, nullptr, nullptr, nullptr, OCO_COMPARATOR_TWO_PASS, st)) return rc;
+    std::vector<double> hr((size_t)n_cand);
+    CU(cudaMemcpyAsync(hr.data(), rc_.p, sizeof(double) * (size_t)n_cand, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    double best = -1.0 / 0.0;
+    for (double v : hr) best = v > best ? v : best;
+    CU(cudaMemcpyAsync(stats_dev, &best, sizeof(double), cudaMemcpyHostToDevice, st));     // exact maximum replaces the bound's
+    CU(cudaStreamSynchronize(st));
+    return OCO_OK;
+}
+
 OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
                           int d, double eta0, double* g_max, double* stats, int comparator_mode, int device) {
     if (!T_grid || !g_max || nT < 0) return fail(OCO_ERR_VALUE, "T_grid / g_max must not be NULL");
     if (n_runs < 0) return fail(OCO_ERR_VALUE, "n_runs must be >= 0");
+    if (comparator_mode < OCO_COMPARATOR_TWO_PASS || comparator_mode > OCO_COMPARATOR_EXACT_MAX)
+        return fail(OCO_ERR_VALUE, "comparator_mode must be OCO_COMPARATOR_TWO_PASS, _LINEAR or _EXACT_MAX");
     DeviceGuard g; if (int rc = g.set(device)) return rc;
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     int rc = OCO_OK;
@@ -582,8 +628,13 @@ OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo
         const int flag = OCO_ALG_FTRL;
         for (int i = 0; i < nT && !rc; ++i) {
             if (T_grid[i] < 0) { rc = fail(OCO_ERR_VALUE, "T_grid[%d] < 0", i); break; }
-            rc = oco_regret_sweep_mode(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T_grid[i], d, -1.0, &flag, &eta0, 1,
-                                       nullptr, nullptr, nullptr, sd.as<double>() + 4 * i, comparator_mode, st);
+            // the pruned exact maximum applies where the single-pass kernel does (2 <= d <= 8); d = 1 is exact in one pass anyway
+            if (comparator_mode == OCO_COMPARATOR_EXACT_MAX && d >= 2 && d <= 8 && n_runs > 0 && T_grid[i] > 0)
+                rc = g_sweep_exact_max_one(T_grid[i], run_lo, n_runs, base_seed, d, eta0, sd.as<double>() + 4 * i, st);
+            else
+                rc = oco_regret_sweep_mode(OCO_FAM_GPATH, base_seed, run_lo, nullptr, n_runs, T_grid[i], d, -1.0, &flag, &eta0, 1,
+                                           nullptr, nullptr, nullptr, sd.as<double>() + 4 * i,
+                                           comparator_mode == OCO_COMPARATOR_LINEAR ? OCO_COMPARATOR_LINEAR : OCO_COMPARATOR_TWO_PASS, st);
         }
         if (!rc && nT > 0 && cudaMemcpyAsync(hs.data(), sd.p, sizeof(double) * 4 * nT, cudaMemcpyDeviceToHost, st) != cudaSuccess)
             rc = fail(OCO_ERR_RUNTIME, "device-to-host copy failed");

@@ -109,6 +109,25 @@ cudaError_t launch_ftrl_scale_table(double* tab, const Etas& eta0, int64_t T, in
     return cudaGetLastError();
 }
 
+__global__ void select_candidates_kernel(const double* __restrict__ regret, int64_t n, int stride, const double* __restrict__ stats_max,
+                                         double margin, int64_t* __restrict__ idx, int* __restrict__ count, int cap) {
+    const double lim = stats_max[0] - margin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (regret[i * stride] >= lim) {
+            const int k = atomicAdd(count, 1);
+            if (k < cap) idx[k] = i;
+        }
+    }
+}
+cudaError_t launch_select_candidates(const double* regret, int64_t n, int stride, const double* stats_max, double margin,
+                                     int64_t* idx, int* count, int cap, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int), st);
+    if (e != cudaSuccess || n <= 0) return e;
+    const unsigned gx = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    select_candidates_kernel<<<gx, 256, 0, st>>>(regret, n, stride, stats_max, margin, idx, count, cap);
+    return cudaGetLastError();
+}
+
 int sweep_gpath_blocks(int64_t n_runs) { return (int)((n_runs + kSweepBlock - 1) / kSweepBlock); }
 
 

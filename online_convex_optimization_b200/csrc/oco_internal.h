@@ -63,6 +63,9 @@ cudaError_t launch_gsweep_hi(const struct SweepArgs& a, int d, cudaStream_t st);
 cudaError_t launch_gsweep_wide(const struct SweepArgs& a, int d, cudaStream_t st); // d = 6, 7, 8
 cudaError_t launch_sweep_iid(const struct SweepArgs& a, int d, cudaStream_t st);
 int sweep_gpath_blocks(int64_t n_runs);
+// candidates for the exact maximum: indices i with regret[i * stride] >= stats_max[0] - margin (at most cap are stored)
+cudaError_t launch_select_candidates(const double* regret, int64_t n, int stride, const double* stats_max, double margin,
+                                     int64_t* idx, int* count, int cap, cudaStream_t st);
 // stats[a*4 + {0,1,2,3}] = max, sum, sumsq, count over all runs (fixed reduction order)
 cudaError_t launch_stats_finalize(const double* partials, int nblocks, int A, int64_t n_runs, double* stats, cudaStream_t st);
 

@@ -16,17 +16,17 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import (COMPARATOR_LINEAR, COMPARATOR_TWO_PASS, FAM_FLIP, FAM_GPATH, FAM_IID, FAM_NOISY, FAM_SWITCH,
+from ._lib import (COMPARATOR_EXACT_MAX, COMPARATOR_LINEAR, COMPARATOR_TWO_PASS, FAM_FLIP, FAM_GPATH, FAM_IID, FAM_NOISY, FAM_SWITCH,
                    OCO_F32, OCO_F64)
 
 SQRT2 = math.sqrt(2.0)
 FAMILIES = {"gpath": FAM_GPATH, "iid": FAM_IID, "noisy": FAM_NOISY, "flip": FAM_FLIP, "switch": FAM_SWITCH}
 class _Comparators(dict):
     def __missing__(self, key):
-        raise ValueError(f"comparator must be 'two_pass' or 'linear' (got {key!r})")
+        raise ValueError(f"comparator must be 'two_pass', 'linear' or (g sweeps only) 'exact_max' (got {key!r})")
 
 
-COMPARATORS = _Comparators({"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR})
+COMPARATORS = _Comparators({"two_pass": COMPARATOR_TWO_PASS, "linear": COMPARATOR_LINEAR, "exact_max": COMPARATOR_EXACT_MAX})
 
 
 def _vp(a) -> C.c_void_p:
@@ -201,7 +201,11 @@ def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int
 
 def g_sweep(T_grid, *, runs: int, base_seed: int = 0, run_lo: int = 0, d: int = 5, eta0: float = SQRT2,
             comparator: str = "two_pass", device: int = 0):
-    """empirical_worst_case_thresholds for runs [run_lo, run_lo+runs) -> (g_max (nT,), stats (nT,4))."""
+    """empirical_worst_case_thresholds for runs [run_lo, run_lo+runs) -> (g_max (nT,), stats (nT,4)).
+    comparator: "two_pass" (literal second pass for every run), "linear" (single pass, 1e-12 class) or "exact_max":
+    the single-pass regret bounds the literal one from above for every run (|q - y| >= 1 - y q), so only the runs whose
+    bound reaches the largest bound take the literal second pass -- g_max equals "two_pass" bit for bit at "linear" speed
+    (the sum / sum of squares in stats are the single-pass ones)."""
     tg = np.ascontiguousarray(T_grid, dtype=np.int64)
     g = np.zeros(tg.size)
     st = np.zeros((tg.size, 4))

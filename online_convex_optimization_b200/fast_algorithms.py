@@ -42,13 +42,16 @@ def simulate_empirical_g_SMART(z: np.ndarray, y: np.ndarray, theta_emp: float, *
 
 
 def empirical_worst_case_thresholds(T_grid: np.ndarray, *, runs: int = 5, base_seed: int = 0,
-                                    comparator: str = "two_pass") -> Dict[int, float]:
+                                    comparator: str = "exact_max") -> Dict[int, float]:
     """fast_algorithms.py:211-247 -- for each T: max over `runs` seeded sequences of the FTRL
     (eta0 = sqrt 2) regret, clamped at 0.  One fused launch per T: sequences are generated on the
     device from the same numpy stream keys (base_seed, T, run) and never stored.
-    `comparator` is this engine's only addition to the reference signature: "two_pass" (default) is the
-    literal fast_algorithms.py:113-114 and reproduces the reference's table bit for bit; "linear" is the
-    single-pass form T/2 - ||theta_T|| (1e-12 * T/2 tolerance, 1.25x faster at T = 1e4; see include/oco_b200.h)."""
+    `comparator` is this engine's only addition to the reference signature.  All three give max_r regret_r:
+    "exact_max" (default): the reference's value BIT FOR BIT at single-pass speed -- the single-pass regret
+    (cum - T/2 + ||theta_T||) is an upper bound of the literal one for every run, so only the runs whose bound reaches
+    the largest bound (typically one) take the literal second pass of fast_algorithms.py:113-114;
+    "two_pass": the literal second pass for every run (same bits, 1.25x slower at T = 1e4);
+    "linear": the single-pass value itself (within 1e-12 * T/2 of the reference; see include/oco_b200.h)."""
     tg = np.asarray(T_grid)
     g, _ = engine.g_sweep(tg, runs=int(runs), base_seed=int(base_seed), comparator=comparator)
     return {int(T): float(v) for T, v in zip(tg, g)}

@@ -21,7 +21,7 @@ def _worker(rank, world, port, n_runs, T, q):
     from online_convex_optimization_b200 import dist as odist
     reg, stats = odist.regret_sweep_sharded("gpath", n_runs, T, 5, [0, 1], [R2, R2], key_a=0, run_lo=0, want_regret=True)
     g = {}
-    for mode in ("two_pass", "linear"):     # T_grid-sharded g(T) sweep: one collective over the (nT, 4) curve
+    for mode in ("two_pass", "linear", "exact_max"):     # T_grid-sharded g(T) sweep: one collective over the (nT, 4) curve
         gg, gst = odist.g_sweep_sharded([100, 250], n_runs, base_seed=0, comparator=mode)
         g[mode] = (gg.cpu().numpy(), gst.cpu().numpy())
     q.put((rank, stats.cpu().numpy(), reg.cpu().numpy(), g))
@@ -57,9 +57,10 @@ def test_sharded_sweep_equals_single_gpu():
         assert np.allclose(st[:, 1], single["stats"][:, 1], rtol=1e-14)
         assert np.allclose(st[:, 2], single["stats"][:, 2], rtol=1e-14)
     # g(T) sweep sharded over the two ranks == the single-GPU sweep (MAX bit-identical), both comparator modes
-    for mode in ("two_pass", "linear"):
+    for mode in ("two_pass", "linear", "exact_max"):
         g1, st1 = engine.g_sweep(np.array([100, 250]), runs=n_runs, base_seed=0, comparator=mode)
         for r in range(world):
             gg, gst = got[r][2][mode]
             assert (gg == g1).all() and (gst[:, 0] == st1[:, 0]).all() and (gst[:, 3] == n_runs).all()
             assert np.allclose(gst[:, 1], st1[:, 1], rtol=1e-13)
+    assert (got[0][2]["exact_max"][0] == got[0][2]["two_pass"][0]).all()      # the pruned maximum IS the literal maximum

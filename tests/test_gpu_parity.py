@@ -577,3 +577,24 @@ def test_round2_paths_edge_cases(eng):
     assert ex["actions"].shape == (2, 1, 12) and (ex["regret"] == 0).all()
     with pytest.raises(ValueError):
         eng.exact_ftl_prefix_batch(np.zeros((1, 3, 257)), np.ones((1, 3)))
+
+
+def test_g_sweep_exact_max_is_bit_exact_at_single_pass_speed(eng):
+    """comparator="exact_max": the single-pass regret is an upper bound of the literal one for every run, so only the
+    candidates for the maximum take the literal second pass -- g(T) equals the two-pass (= reference) value bit for bit."""
+    for d, Tg, runs, seed in ((5, [100, 257, 1000], 700, 0), (2, [64, 300], 300, 3), (8, [120], 200, 1), (3, [1, 2, 33], 40, 9)):
+        Tg = np.array(Tg)
+        if d <= 5:
+            g0, st0 = eng.g_sweep(Tg, runs=runs, base_seed=seed, d=d)
+        else:       # d = 6..8 has no fused two-pass sweep: the oracle gives the literal values
+            g0 = np.array([max(0.0, O.regret_sweep(seed, int(T), 0, runs, d, [0], [R2]).max()) for T in Tg])
+        g1, st1 = eng.g_sweep(Tg, runs=runs, base_seed=seed, d=d, comparator="exact_max")
+        assert (bits(g1) == bits(g0)).all(), (d, g1, g0)
+        assert (st1[:, 3] == runs).all()
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    want = O.empirical_worst_case_thresholds(np.array([100, 400]), runs=300, base_seed=2)
+    assert fa.empirical_worst_case_thresholds(np.array([100, 400]), runs=300, base_seed=2) == want           # default = exact_max
+    assert fa.empirical_worst_case_thresholds(np.array([100, 400]), runs=300, base_seed=2, comparator="two_pass") == want
+    # full length: 64 runs at T = 1e4 against the oracle
+    g, _ = eng.g_sweep(np.array([10_000]), runs=64, base_seed=0, comparator="exact_max")
+    assert g[0] == max(0.0, O.regret_sweep(0, 10_000, 0, 64, 5, [0], [R2]).max())

@@ -248,7 +248,7 @@ static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint
     Pcg64 s; PcgInc inc;
     pcg_seed3(s, inc, ka, (uint64_t)T, kc);
     Pcg64 s0 = s;
-    for (int n = 0; n < T * D; ++n) zig_skip2(tb, s, inc);
+    for (int64_t n = 0; n < (int64_t)T * D; ++n) zig_skip2(tb, s, inc);
     LabelCursor lab; lab.s = s; lab.cur = 0;
     s = s0;
     double C = 0.0;

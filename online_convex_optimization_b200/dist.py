@@ -92,11 +92,12 @@ def _device_g_stats(T_grid, lo, n, base_seed, d, eta0, comparator):
 
 
 def g_sweep_sharded(T_grid, runs: int, *, base_seed: int = 0, d: int = 5, eta0: float = 2.0 ** 0.5,
-                    comparator: str = "two_pass", group=None, stats_fn=None):
+                    comparator: str = "exact_max", group=None, stats_fn=None):
     """fast_algorithms.empirical_worst_case_thresholds (fast_algorithms.py:211-247) with the `runs` sharded over the
     ranks of `group` (contiguous blocks, every T of a run on the same rank) and ONE collective over the (nT, 4)
     per-T statistics.  Returns (g (nT,) = max(0, max_r regret), stats (nT, 4) = max, sum, sumsq, count) on every rank;
-    g is bit-identical for any number of ranks (MAX is order independent).  `stats_fn(T_grid, lo, n)` replaces the
+    g is bit-identical for any number of ranks (MAX is order independent) and, with the default comparator="exact_max"
+    (or "two_pass"), bit-identical to the reference's value.  `stats_fn(T_grid, lo, n)` replaces the
     device sweep in the CPU (gloo) tests of this host logic."""
     import torch
     import torch.distributed as dist

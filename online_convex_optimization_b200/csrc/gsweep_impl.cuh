@@ -266,9 +266,23 @@ static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint
 // requested at the end of step t and lands in shared memory without touching a register, so no scoreboard wait can be
 // scheduled next to the request (a register prefetch was rotated by the compiler into "load, then copy at the end of
 // the same step": 26 % of all stall samples on that copy).  Every thread reads only the slots it filled itself.
+//
+// Round-2 diet (profiles/r02_ncu_summary.md, C3: 395 -> ~300 warp-instructions per warp-step):
+//   * the labels of a sequence (numpy draws them after all of its normals) are drawn by the GENERATING side right
+//     after its last row and parked, 32 per word, behind the rows in the slab: the play side carries no PCG64 stream
+//     (12 registers, one 50 % taken branch per step) and decodes a label with a shift;
+//   * with several FTRL variants per thread the -(eta0/sqrt(t)) table rows are staged per warp in shared memory,
+//     32 steps at a time (each lane copies one row with cp.async; the step reads them as broadcast LDS.128): no
+//     per-step global loads, no prefetch registers (16 at NF = 8), no long-scoreboard wait on the table;
+//   * d = 1: |z| <= 1, |x| <= 1, y = +-1 make sign(q - y) = -y whenever q != y, so the step +-0.5 z is formed once
+//     per row from the label's sign and shared by all variants.
+// The freed registers stop the compiler from rematerialising addresses every step (~50 instructions).
 constexpr int kRing = 4;
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -280,29 +294,41 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef OCO_GSWEEP_MIN_BLOCKS_NF
 #define OCO_GSWEEP_MIN_BLOCKS_NF 4          // several FTRL variants per thread: more registers, fewer resident CTAs
 #endif
+constexpr int kLabelsPerWord = 32;          // packed labels: bit i of word w = 1 iff y[32 w + i] = -1
+constexpr int kTabBlock = 32;               // steps of the FTRL scale table staged at a time (one row per lane)
+
+// bytes of one slab (rows of one item, then its packed labels); two per resident CTA
+__host__ __device__ inline size_t gsweep_slab_bytes(int64_t T, int D) {
+    return (size_t)T * D * kSweepBlock * sizeof(double) + (size_t)((T + kLabelsPerWord - 1) / kLabelsPerWord) * kSweepBlock * sizeof(uint32_t);
+}
 
 template <int D, int NFTL, int NF>
 __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : OCO_GSWEEP_MIN_BLOCKS_NF) * kSweepBlockScale) gsweep_kernel(const SweepArgs p) {
     static_assert(D >= 1 && D <= 8, "thread-per-sequence kernel: theta lives in registers");
+    // scale rows through shared memory (16-byte copies) where the static 48 KB allow it (not d = 7, 8 with NF = 8)
+    constexpr bool kStageTab = NF >= 2 && (NF % 2 == 0) &&
+        kRing * D * kSweepBlock * 8 + (kSweepBlock / 32) * 2 * kTabBlock * NF * 8 + (int)sizeof(ZigTab2) + 256 <= 48 * 1024;
     __shared__ ZigTab2 tb;
     __shared__ double red[kSweepBlock / 32][3];
     __shared__ double ring[kRing][D][kSweepBlock];              // [slot][coordinate][thread]: conflict-free LDS.64
+    __shared__ __align__(16) double sct[kStageTab ? kSweepBlock / 32 : 1][2][kStageTab ? kTabBlock : 1][kStageTab ? NF : 1];
     zig_tab2_load(tb);
     const int T = p.T, A = p.plan.A, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int groups = p.plan.groups;
     constexpr unsigned mask = 0xffffffffu;
     // two slabs per CTA: round r writes slab r & 1 (generation of item r) and reads slab (r - 1) & 1 (play of item r - 1)
-    const int64_t slab_elems = (int64_t)T * D * kSweepBlock;
-    double* __restrict__ slab0 = reinterpret_cast<double*>(p.slab_z) + (int64_t)blockIdx.x * 2 * slab_elems + tid;
+    const size_t slab_bytes = gsweep_slab_bytes(T, D);
+    const int64_t row_bytes = (int64_t)T * D * kSweepBlock * sizeof(double);
+    char* const slab_base = reinterpret_cast<char*>(p.slab_z) + (size_t)blockIdx.x * 2 * slab_bytes;
+    const int nw = (T + kLabelsPerWord - 1) / kLabelsPerWord;
 
     // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int64_t n_my = p.n_items > blockIdx.x ? (p.n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    // ---- state of the sequence being PLAYED (item r - 1)
-    LabelCursorLA lab; lab.g.s.hi = 0; lab.g.s.lo = 0; lab.g.rn = 0; lab.cur = 0;
-    PcgInc incB; incB.hi = 0; incB.lo = 0;
+    // ---- the sequence being PLAYED (item r - 1)
     int64_t chunkB = 0, bB = 0; int gB = 0; bool activeB = false;
-    // ---- state of the sequence being GENERATED (item r)
+    // ---- the sequence being GENERATED (item r)
     GenLA genA; genA.s.hi = 0; genA.s.lo = 0; genA.rn = 0;
     PcgInc incA; incA.hi = 0; incA.lo = 0;
 
@@ -319,8 +345,11 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             pcg_seed3(genA.s, incA, ka, (uint64_t)T, kc);
             genA.rn = pcg_next64(genA.s, incA);
         }
-        double* __restrict__ zw = slab0 + (r & 1) * slab_elems;                 // generation writes here
-        const double* __restrict__ zr = slab0 + ((r + 1) & 1) * slab_elems;     // play reads the other one
+        char* const slabW = slab_base + (size_t)(r & 1) * slab_bytes;               // generation writes here
+        const char* const slabR = slab_base + (size_t)((r + 1) & 1) * slab_bytes;   // play reads the other one
+        double* __restrict__ zw = reinterpret_cast<double*>(slabW) + tid;
+        const double* __restrict__ zr = reinterpret_cast<const double*>(slabR) + tid;
+        const uint32_t* __restrict__ lr = reinterpret_cast<const uint32_t*>(slabR + row_bytes) + tid;
 
         // play state (fast_algorithms.py:95-97); theta2 = 2*theta, S = sum |q - y|
         double th2r[NF][D], Sr[NF];
@@ -343,14 +372,23 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
         double cand[4] = {0.0, 0.0, 0.0, 0.0};                  // sum |c*z - y| for c = +1, -1, +w, -w
         const double kW = __longlong_as_double(0x3fefffffffffffffLL);
 
-        // the row and the FTRL scales of step t are fetched at the END of step t - 1 into the registers step t
-        // reads them from (no copy the compiler could sink to the loop end): a whole generation step hides the HBM latency
-        double scn[NF];
+        // FTRL scales of the step: NF >= 2 -> staged per warp in shared memory, kTabBlock steps at a time (lane l copies
+        // the row of step t0 + l); NF == 1 -> one register fetched a step ahead
+        double scn1 = 0.0;
+        auto stage_tab = [&](int t0, int buf) {
+            if constexpr (kStageTab) {
+                const int t = t0 + lane;
+                if (t < T) {
 #pragma unroll
-        for (int k = 0; k < NF; ++k) scn[k] = (doB && T > 0) ? __ldg(tp + k) : 0.0;
-        if (doB) {                                              // rows 0 .. kRing-2 of the sequence to play: one group per row
+                    for (int k = 0; k < NF; k += 2) cp_async16(&sct[warp][buf][lane][k], tp + (int64_t)t * NF + k);
+                }
+            }
+        };
+        if (doB) {
+            if constexpr (kStageTab) { stage_tab(0, 0); cp_async_commit(); }
+            else if (T > 0) scn1 = __ldg(tp);
 #pragma unroll
-            for (int i = 0; i < kRing - 1; ++i) {
+            for (int i = 0; i < kRing - 1; ++i) {               // rows 0 .. kRing-2 of the sequence to play: one group per row
                 if (i < T) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) cp_async8(&ring[i][j][tid], zr + ((int64_t)i * D + j) * kSweepBlock);
@@ -358,137 +396,182 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 cp_async_commit();
             }
         }
+        const double* __restrict__ zrn = zr + (int64_t)(kRing - 1) * D * kSweepBlock;   // next row to request
+        uint32_t wnext = (doB && T > 0) ? __ldcg(lr) : 0u;
+        int slot = 0;                                           // ring slot of row t
 
-        for (int t = 0; t < T; ++t) {
-            // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
-            if (doA) {
-                double z[D];
-                gpath_row_la<D>(tb, genA, incA, z);
-#pragma unroll
-                for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
-                zw += D * kSweepBlock;
-            }
-            // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
+        for (int t0 = 0; t0 < T; t0 += kTabBlock) {
+            const int tn = min(kTabBlock, T - t0);
+            uint32_t lw = wnext;                                // labels of steps t0 .. t0 + 31 (bit = 1: y = -1)
             if (doB) {
-                cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
-                double z[D];
+                if (t0 + kLabelsPerWord < T) wnext = __ldcg(lr + (int64_t)((t0 >> 5) + 1) * kSweepBlock);
+                if constexpr (kStageTab) {
+                    cp_async_wait<kRing - 2>();                 // this lane's copy of the block's scale rows has landed ...
+                    __syncwarp();                               // ... and so have the other lanes' (all past the previous block)
+                    stage_tab(t0 + kTabBlock, ((t0 / kTabBlock) + 1) & 1);      // joins the commit group of step t0
+                }
+            }
+            const double* __restrict__ scb = &sct[kStageTab ? warp : 0][kStageTab ? (t0 / kTabBlock) & 1 : 0][0][0];
+
+            for (int i = 0; i < tn; ++i) {
+                const int t = t0 + i;
+                // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
+                if (doA) {
+                    double z[D];
+                    gpath_row_la<D>(tb, genA, incA, z);
 #pragma unroll
-                for (int j = 0; j < D; ++j) z[j] = ring[t & (kRing - 1)][j][tid];
-                const double y = lab.next(t, incB);
-                if constexpr (D == 1) {
-                    // (d = 1 keeps theta itself in th2*: one shared hz = 0.5*z per step beats halving NF scales)
-                    const double z0 = z[0], hz0 = 0.5 * z0;
-                    const double pw = z0 * kW;                      // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
-                    cand[0] = cand[0] + fabs(z0 - y);
-                    cand[1] = cand[1] + fabs(z0 + y);
-                    cand[2] = cand[2] + fabs(pw - y);
-                    cand[3] = cand[3] + fabs(pw + y);
-                    if (NFTL > 0 && do_ftl) {
-                        // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal;
-                        // th == 0 plays -0.0 instead of 0.0 (z*x is a zero either way and df = -y exactly)
-                        const double n2 = th2l[0] * th2l[0];
-                        double rc = rcp_inrange(th2l[0]);           // garbage unless 1e-290 <= n2 <= 1e290
-                        if (!(n2 >= 1e-290 && n2 <= 1e290)) rc = (n2 == 0.0) ? 1.0 : 1.0 / sqrt(n2);
-                        const double x = -fabs(rc) * th2l[0];
-                        const double df = z0 * x - y;
-                        Sl = Sl + fabs(df);
-                        const int sgn = __double2hiint(df) & 0x80000000;
-                        const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
-                        if (fabs(df) > 0.0) th2l[0] = th2l[0] + gz;         // zero / NaN diff: no step (fast_algorithms.py:27-34)
-                    }
-                    // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
-                    // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
-                    // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
-                    // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
-                    constexpr int H = NF >= 4 ? NF / 2 : NF;
+                    for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
+                    zw += D * kSweepBlock;
+                }
+                // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
+                if (doB) {
+                    cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
+                    double z[D];
 #pragma unroll
-                    for (int h0 = 0; h0 < NF; h0 += H) {
-                        double x1[H], n2v[H];
-                        int top = 0;                                // max over the half of the high word of n2 (n2 >= 0 or NaN)
+                    for (int j = 0; j < D; ++j) z[j] = ring[slot][j][tid];
+                    const int yhi = (int)((lw << 31) | 0x3ff00000u);    // y = -1.0 iff the label bit is set
+                    lw >>= 1;
+                    const double y = __hiloint2double(yhi, 0);
+                    double scn[NF];
+                    if constexpr (kStageTab) {
 #pragma unroll
-                        for (int k = 0; k < H; ++k) {
-                            x1[k] = scn[h0 + k] * th2r[h0 + k][0];
-                            n2v[k] = x1[k] * x1[k];
-                            top = max(top, __double2hiint(n2v[k]));
+                        for (int k = 0; k < NF; k += 2) {
+                            const double2 v = *reinterpret_cast<const double2*>(scb + i * NF + k);
+                            scn[k] = v.x; scn[k + 1] = v.y;
                         }
-                        if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
-                            if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
+                    } else {
 #pragma unroll
-                                for (int k = 0; k < H; ++k) {
-                                    double xx[1] = {x1[k]};
-                                    project_unit_ball<1>(xx, n2v[k], mask);
-                                    x1[k] = xx[0];
-                                }
-                            } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
+                        for (int k = 0; k < NF; ++k) scn[k] = (NF == 1) ? scn1 : __ldg(tp + (int64_t)t * NF + k);
+                    }
+                    if constexpr (D == 1) {
+                        // (d = 1 keeps theta itself in th2*: one shared hz = 0.5*z per step beats halving NF scales)
+                        // |z| <= 1 (clipped row), |x| <= 1 (projected action), y = +-1: q - y has the sign of -y unless it
+                        // is exactly 0 (or NaN), so the gradient step of EVERY variant is gz = -y * 0.5 z or nothing
+                        const double z0 = z[0], hz0 = 0.5 * z0;
+                        const double gz = __hiloint2double(__double2hiint(hz0) ^ (~yhi & 0x80000000), __double2loint(hz0));
+                        const double pw = z0 * kW;                      // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
+                        cand[0] = cand[0] + fabs(z0 - y);
+                        cand[1] = cand[1] + fabs(z0 + y);
+                        cand[2] = cand[2] + fabs(pw - y);
+                        cand[3] = cand[3] + fabs(pw + y);
+                        if (NFTL > 0 && do_ftl) {
+                            // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal;
+                            // th == 0 plays -0.0 instead of 0.0 (z*x is a zero either way and df = -y exactly)
+                            const double n2 = th2l[0] * th2l[0];
+                            double rc = rcp_inrange(th2l[0]);           // garbage unless 1e-290 <= n2 <= 1e290
+                            const bool odd = !(n2 >= 1e-290 && n2 <= 1e290);
+                            if (odd) rc = (n2 == 0.0) ? 1.0 : 1.0 / sqrt(n2);
+                            const double x = -fabs(rc) * th2l[0];
+                            const double df = z0 * x - y;
+                            Sl = Sl + fabs(df);
+                            double g = gz;
+                            // (th*th under- or overflowed: |x| <= 1 is not guaranteed there, take the sign from df itself)
+                            if (odd) g = __hiloint2double(__double2hiint(hz0) ^ (__double2hiint(df) & 0x80000000), __double2loint(hz0));
+                            if (fabs(df) > 0.0) th2l[0] = th2l[0] + g;          // zero / NaN diff: no step (fast_algorithms.py:27-34)
+                        }
+                        // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
+                        // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
+                        // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
+                        // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
+                        constexpr int H = NF >= 4 ? NF / 2 : NF;
 #pragma unroll
-                                for (int k = 0; k < H; ++k) {
-                                    const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
-                                    if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
+                        for (int h0 = 0; h0 < NF; h0 += H) {
+                            double x1[H], n2v[H];
+                            int top = 0;                                // max over the half of the high word of n2 (n2 >= 0 or NaN)
+#pragma unroll
+                            for (int k = 0; k < H; ++k) {
+                                x1[k] = scn[h0 + k] * th2r[h0 + k][0];
+                                n2v[k] = x1[k] * x1[k];
+                                top = max(top, __double2hiint(n2v[k]));
+                            }
+                            if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
+                                if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
+#pragma unroll
+                                    for (int k = 0; k < H; ++k) {
+                                        double xx[1] = {x1[k]};
+                                        project_unit_ball<1>(xx, n2v[k], mask);
+                                        x1[k] = xx[0];
+                                    }
+                                } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
+#pragma unroll
+                                    for (int k = 0; k < H; ++k) {
+                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
+                                        if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
+                                    }
                                 }
                             }
-                        }
 #pragma unroll
-                        for (int k = 0; k < H; ++k) {
-                            const double df = z0 * x1[k] - y;
-                            Sr[h0 + k] = Sr[h0 + k] + fabs(df);
-                            const int sgn = __double2hiint(df) & 0x80000000;
-                            const double gz = __hiloint2double(__double2hiint(hz0) ^ sgn, __double2loint(hz0));
-                            if (fabs(df) > 0.0) th2r[h0 + k][0] = th2r[h0 + k][0] + gz;
+                            for (int k = 0; k < H; ++k) {
+                                const double df = z0 * x1[k] - y;
+                                Sr[h0 + k] = Sr[h0 + k] + fabs(df);
+                                if (fabs(df) > 0.0) th2r[h0 + k][0] = th2r[h0 + k][0] + gz;
+                            }
                         }
+                    } else {
+                    if (NFTL > 0 && do_ftl) {
+                        // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
+                        double x[D];
+                        ftl_action<D>(th2l, x);
+                        const double df = dot_seq<D>(z, x) - y;
+                        Sl = Sl + fabs(df);
+                        const int dhi = __double2hiint(df);
+                        okl &= dhi ^ yhi;
+                        if (df > 0.0 || df < 0.0) {
+                            const int sgn = dhi & 0x80000000;
+#pragma unroll
+                            for (int j = 0; j < D; ++j)
+                                th2l[j] = th2l[j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                        } else zero_df = true;
                     }
-                } else {
-                const int yhi = __double2hiint(y);
-                if (NFTL > 0 && do_ftl) {
-                    // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
-                    double x[D];
-                    ftl_action<D>(th2l, x);
-                    const double df = dot_seq<D>(z, x) - y;
-                    Sl = Sl + fabs(df);
-                    const int dhi = __double2hiint(df);
-                    okl &= dhi ^ yhi;
-                    if (df > 0.0 || df < 0.0) {
-                        const int sgn = dhi & 0x80000000;
 #pragma unroll
-                        for (int j = 0; j < D; ++j)
-                            th2l[j] = th2l[j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
-                    } else zero_df = true;
-                }
+                    for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
+                        const double sch = 0.5 * scn[k];             // (0.5*scale) * theta2 == scale * theta
+                        double x[D];
 #pragma unroll
-                for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
-                    const double sch = 0.5 * scn[k];             // (0.5*scale) * theta2 == scale * theta
-                    double x[D];
+                        for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
+                        double n2 = x[0] * x[0];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
-                    double n2 = x[0] * x[0];
+                        for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                        project_unit_ball<D>(x, n2, mask);
+                        const double df = dot_seq<D>(z, x) - y;
+                        Sr[k] = Sr[k] + fabs(df);
+                        const int dhi = __double2hiint(df);
+                        okr[k] &= dhi ^ yhi;
+                        if (df > 0.0 || df < 0.0) {
+                            const int sgn = dhi & 0x80000000;
 #pragma unroll
-                    for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
-                    project_unit_ball<D>(x, n2, mask);
-                    const double df = dot_seq<D>(z, x) - y;
-                    Sr[k] = Sr[k] + fabs(df);
-                    const int dhi = __double2hiint(df);
-                    okr[k] &= dhi ^ yhi;
-                    if (df > 0.0 || df < 0.0) {
-                        const int sgn = dhi & 0x80000000;
+                            for (int j = 0; j < D; ++j)
+                                th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                        } else zero_df = true;
+                    }
+                    }
+                    if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
 #pragma unroll
-                        for (int j = 0; j < D; ++j)
-                            th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
-                    } else zero_df = true;
-                }
-                }
-                tp += NF;
-                if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
-#pragma unroll
-                    for (int j = 0; j < D; ++j)
-                        cp_async8(&ring[(t + kRing - 1) & (kRing - 1)][j][tid], zr + ((int64_t)(t + kRing - 1) * D + j) * kSweepBlock);
-                }
-                cp_async_commit();
-                if (t + 1 < T) {
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) scn[k] = __ldg(tp + k);
+                        for (int j = 0; j < D; ++j) cp_async8(&ring[(slot + kRing - 1) & (kRing - 1)][j][tid], zrn + j * kSweepBlock);
+                        zrn += D * kSweepBlock;
+                    }
+                    cp_async_commit();
+                    slot = (slot + 1) & (kRing - 1);
+                    if constexpr (NF == 1) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
                 }
             }
         }
 
+        // ---- labels of the generated item: numpy's choice([-1, 1], T) continues the stream after the last normal; one
+        // 32-bit draw per label, low half of each raw first (rng_numpy.cuh::LabelCursor), 16 raws per packed word
+        if (doA) {
+            uint32_t* __restrict__ lwp = reinterpret_cast<uint32_t*>(slabW + row_bytes) + tid;
+            for (int w = 0; w < nw; ++w) {
+                uint32_t word = 0;
+#pragma unroll 4
+                for (int i = 0; i < kLabelsPerWord / 2; ++i) {      // (draws past label T - 1 are harmless: the stream ends here)
+                    const uint64_t raw = la_take(genA, incA);
+                    const uint32_t lo = (uint32_t)raw, hi = (uint32_t)(raw >> 32);
+                    word = (word >> 2) | ((~lo >> 1) & 0x40000000u) | (~hi & 0x80000000u);
+                }
+                __stcg(lwp + (int64_t)w * kSweepBlock, word);
+            }
+        }
         // ---- comparator, results and per-chunk statistics of the played item
         if (r > 0) {                                            // (uniform over the CTA: the reduction below synchronises)
             const int nf = min(NF, p.plan.n_ftrl - gB * NF);
@@ -547,8 +630,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             }
             // per-chunk (max, sum, sumsq) of the regrets, fixed order (same layout as sweep_kernel)
             if (p.partials) {
-                const int lane = tid & 31, warp = tid >> 5;
-                const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
+                                const int nslots = (nf > 0 ? nf : 0) + (do_ftl ? 1 : 0);
                 for (int sidx = 0; sidx < nslots; ++sidx) {
                     const bool is_ftl = do_ftl && sidx == nslots - 1;
                     double rg = reg_l;
@@ -581,8 +663,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             }
         }
 
-        // ---- hand over: the sequence just generated is played next; numpy's choice([-1, 1], T) continues its stream
-        lab.g = genA; lab.cur = 0; incB = incA;
+        // ---- hand over: the sequence just generated is played next
         chunkB = chunkA; gB = gA; bB = bA; activeB = activeA;
     }
 }
@@ -599,7 +680,7 @@ static cudaError_t launch_gsweep_cfg(SweepArgs a, cudaStream_t st) {
     const int64_t chunks = (a.B + kSweepBlock - 1) / kSweepBlock;
     a.n_items = chunks * a.plan.groups;
     int64_t grid = std::min<int64_t>(a.n_items, (int64_t)sms * std::max(per_sm, 1));
-    const size_t per_cta = 2 * (size_t)a.T * D * kSweepBlock * sizeof(double);
+    const size_t per_cta = 2 * gsweep_slab_bytes(a.T, D);
     if (per_cta > 0) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {

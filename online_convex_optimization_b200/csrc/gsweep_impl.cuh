@@ -224,6 +224,67 @@ __device__ __forceinline__ void gpath_row_la(const ZigTab2& tb, GenLA& g, const 
 #pragma unroll
     for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
 }
+// ---- the same generator reading the tables through a PINNED 32-bit shared-memory address: ptxas otherwise
+// rematerialises the shared-window base of a static __shared__ object (S2UR SR_CgaCtaId + UMOV + ULEA) at every use
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
+__device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
+    ulonglong2 v; asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64_v(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 lds_v2f64_v(uint32_t a) {
+    double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
+}
+__device__ __forceinline__ bool zig_try_a(uint32_t tba, uint64_t r, double& x, int& idx, uint64_t& mag) {
+    idx = (int)(r & 0xff);
+    mag = ((r >> 9) & 0x000fffffffffffffULL) | 0x4330000000000000ULL;
+    const ulonglong2 wk = lds_v2u64(tba + (((uint32_t)r << 4) & 0xff0u));
+    const int sgn = (int)(((uint32_t)r << 23) & 0x80000000u);                    // bit 8 of r -> sign bit
+    const double w = __hiloint2double((int)(wk.x >> 32) ^ sgn, (int)(uint32_t)wk.x);   // (+-wi): (-a)*b == -(a*b)
+    x = (__longlong_as_double((long long)mag) - 4503599627370496.0) * w;
+    return mag < wk.y;
+}
+static __device__ __forceinline__ double zig_slow_la_a(uint32_t tba, GenLA& g, const PcgInc& inc, int idx, uint64_t mag, double x) {
+    for (;;) {
+        if (idx == 0) {
+            const ZigTailLARet o = zig_tail_la(g.s.hi, g.s.lo, g.rn, inc.hi, inc.lo, mag & 0x000fffffffffffffULL);
+            g.s.hi = o.hi; g.s.lo = o.lo; g.rn = o.rn;
+            return o.x;
+        }
+        const uint32_t fa = tba + (uint32_t)offsetof(ZigTab2, fi) + (uint32_t)idx * 8u;
+        const double f1 = lds_f64(fa), f0 = lds_f64(fa - 8u);
+        const double yv = (f0 - f1) * la_double(g, inc) + f1;
+        const double arg = -0.5 * x * x;
+        const double ef = (double)__expf((float)arg);
+        const bool sure_yes = yv < ef * (1.0 - 1e-5), sure_no = yv > ef * (1.0 + 1e-5);
+        bool accept = sure_yes;
+        if (!sure_yes && !sure_no) accept = zig_wedge_exact(yv, arg);
+        if (accept) return x;
+        if (zig_try_a(tba, la_take(g, inc), x, idx, mag)) return x;     // rejected: a fresh attempt
+    }
+}
+__device__ __forceinline__ double zig_normal_la_a(uint32_t tba, GenLA& g, const PcgInc& inc) {
+    const uint64_t r = la_take(g, inc);
+    double x; int idx; uint64_t mag;
+    if (zig_try_a(tba, r, x, idx, mag)) return x;
+    return zig_slow_la_a(tba, g, inc, idx, mag, x);
+}
+template <int D>
+__device__ __forceinline__ void gpath_row_la_a(uint32_t tba, GenLA& g, const PcgInc& inc, double (&z)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) z[j] = zig_normal_la_a(tba, g, inc);
+    if constexpr (D == 1) {
+        // z * fl(1/max(|z|, 1)): untouched unless |z| > 1 (z * 1.0 == z); sqrt(fl(z*z)) == |z| there, and
+        // z * fl(1/|z|) == z * |fl(1/z)| (the reciprocal is odd); rcp_inrange's result is only used where 1 < |z| < 1e3
+        const double rc = fabs(rcp_inrange(z[0]));
+        if (fabs(z[0]) > 1.0) z[0] = z[0] * rc;
+    } else {
+        const double nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
+        const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
+    }
+}
 // Generator.choice([-1.0, 1.0], size=T) continuing a lookahead stream: one 32-bit draw per label, low half of
 // each raw first, then the high half; label = top bit (rng_numpy.cuh::LabelCursor with the raw prefetched)
 struct LabelCursorLA {
@@ -278,8 +339,16 @@ static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint
 //     per row from the label's sign and shared by all variants.
 // The freed registers stop the compiler from rematerialising addresses every step (~50 instructions).
 constexpr int kRing = 4;
+// th += g iff df is neither zero nor NaN, as ONE compare and ONE predicated add (the compiler's own choice is an
+// unconditional add and two selects)
+__device__ __forceinline__ void add_if_nonzero(double& th, double df, double g) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.f64 p, %1, 0d0000000000000000;\n\t@p add.rn.f64 %0, %0, %2;\n\t}" : "+d"(th) : "d"(df), "d"(g));
+}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8a(uint32_t smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
@@ -315,6 +384,11 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
     zig_tab2_load(tb);
     const int T = p.T, A = p.plan.A, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    // 32-bit shared-memory addresses, pinned in registers (see pin_u32)
+    const uint32_t tba = pin_u32((uint32_t)__cvta_generic_to_shared(&tb));
+    const uint32_t ringa = pin_u32((uint32_t)__cvta_generic_to_shared(&ring[0][0][tid]));
+    const uint32_t scta = pin_u32((uint32_t)__cvta_generic_to_shared(&sct[kStageTab ? warp : 0][0][0][0]));
+    constexpr uint32_t kSlotBytes = D * kSweepBlock * 8, kRingBytes = kRing * kSlotBytes, kTabBufBytes = kTabBlock * NF * 8;
     const int groups = p.plan.groups;
     constexpr unsigned mask = 0xffffffffu;
     // two slabs per CTA: round r writes slab r & 1 (generation of item r) and reads slab (r - 1) & 1 (play of item r - 1)
@@ -391,14 +465,14 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             for (int i = 0; i < kRing - 1; ++i) {               // rows 0 .. kRing-2 of the sequence to play: one group per row
                 if (i < T) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) cp_async8(&ring[i][j][tid], zr + ((int64_t)i * D + j) * kSweepBlock);
+                    for (int j = 0; j < D; ++j) cp_async8a(ringa + i * kSlotBytes + j * (kSweepBlock * 8), zr + ((int64_t)i * D + j) * kSweepBlock);
                 }
                 cp_async_commit();
             }
         }
         const double* __restrict__ zrn = zr + (int64_t)(kRing - 1) * D * kSweepBlock;   // next row to request
         uint32_t wnext = (doB && T > 0) ? __ldcg(lr) : 0u;
-        int slot = 0;                                           // ring slot of row t
+        uint32_t slot = 0, slotn = (kRing - 1) * kSlotBytes;    // byte offsets of the ring slots of row t and of row t + kRing - 1
 
         for (int t0 = 0; t0 < T; t0 += kTabBlock) {
             const int tn = min(kTabBlock, T - t0);
@@ -411,14 +485,14 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     stage_tab(t0 + kTabBlock, ((t0 / kTabBlock) + 1) & 1);      // joins the commit group of step t0
                 }
             }
-            const double* __restrict__ scb = &sct[kStageTab ? warp : 0][kStageTab ? (t0 / kTabBlock) & 1 : 0][0][0];
+            uint32_t sca = scta + (kStageTab ? ((t0 / kTabBlock) & 1) * kTabBufBytes : 0u);      // scale row of step t
 
             for (int i = 0; i < tn; ++i) {
                 const int t = t0 + i;
                 // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
                 if (doA) {
                     double z[D];
-                    gpath_row_la<D>(tb, genA, incA, z);
+                    gpath_row_la_a<D>(tba, genA, incA, z);
 #pragma unroll
                     for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
                     zw += D * kSweepBlock;
@@ -428,7 +502,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
                     double z[D];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) z[j] = ring[slot][j][tid];
+                    for (int j = 0; j < D; ++j) z[j] = lds_f64_v(ringa + slot + j * (kSweepBlock * 8));
                     const int yhi = (int)((lw << 31) | 0x3ff00000u);    // y = -1.0 iff the label bit is set
                     lw >>= 1;
                     const double y = __hiloint2double(yhi, 0);
@@ -436,9 +510,10 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     if constexpr (kStageTab) {
 #pragma unroll
                         for (int k = 0; k < NF; k += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(scb + i * NF + k);
+                            const double2 v = lds_v2f64_v(sca + k * 8);
                             scn[k] = v.x; scn[k + 1] = v.y;
                         }
+                        sca += NF * 8;
                     } else {
 #pragma unroll
                         for (int k = 0; k < NF; ++k) scn[k] = (NF == 1) ? scn1 : __ldg(tp + (int64_t)t * NF + k);
@@ -467,7 +542,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                             double g = gz;
                             // (th*th under- or overflowed: |x| <= 1 is not guaranteed there, take the sign from df itself)
                             if (odd) g = __hiloint2double(__double2hiint(hz0) ^ (__double2hiint(df) & 0x80000000), __double2loint(hz0));
-                            if (fabs(df) > 0.0) th2l[0] = th2l[0] + g;          // zero / NaN diff: no step (fast_algorithms.py:27-34)
+                            add_if_nonzero(th2l[0], df, g);                     // zero / NaN diff: no step (fast_algorithms.py:27-34)
                         }
                         // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
                         // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
@@ -504,7 +579,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                             for (int k = 0; k < H; ++k) {
                                 const double df = z0 * x1[k] - y;
                                 Sr[h0 + k] = Sr[h0 + k] + fabs(df);
-                                if (fabs(df) > 0.0) th2r[h0 + k][0] = th2r[h0 + k][0] + gz;
+                                add_if_nonzero(th2r[h0 + k][0], df, gz);
                             }
                         }
                     } else {
@@ -547,11 +622,12 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     }
                     if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
 #pragma unroll
-                        for (int j = 0; j < D; ++j) cp_async8(&ring[(slot + kRing - 1) & (kRing - 1)][j][tid], zrn + j * kSweepBlock);
+                        for (int j = 0; j < D; ++j) cp_async8a(ringa + slotn + j * (kSweepBlock * 8), zrn + j * kSweepBlock);
                         zrn += D * kSweepBlock;
                     }
                     cp_async_commit();
-                    slot = (slot + 1) & (kRing - 1);
+                    slot = slot + kSlotBytes == kRingBytes ? 0u : slot + kSlotBytes;
+                    slotn = slotn + kSlotBytes == kRingBytes ? 0u : slotn + kSlotBytes;
                     if constexpr (NF == 1) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
                 }
             }

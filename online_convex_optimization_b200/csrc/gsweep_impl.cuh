@@ -375,7 +375,7 @@ template <int D, int NFTL, int NF>
 __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS : OCO_GSWEEP_MIN_BLOCKS_NF) * kSweepBlockScale) gsweep_kernel(const SweepArgs p) {
     static_assert(D >= 1 && D <= 8, "thread-per-sequence kernel: theta lives in registers");
     // scale rows through shared memory (16-byte copies) where the static 48 KB allow it (not d = 7, 8 with NF = 8)
-    constexpr bool kStageTab = NF >= 2 && (NF % 2 == 0) &&
+    constexpr bool kStageTab = (NF == 1 || NF % 2 == 0) &&
         kRing * D * kSweepBlock * 8 + (kSweepBlock / 32) * 2 * kTabBlock * NF * 8 + (int)sizeof(ZigTab2) + 256 <= 48 * 1024;
     __shared__ ZigTab2 tb;
     __shared__ double red[kSweepBlock / 32][3];
@@ -453,14 +453,17 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
             if constexpr (kStageTab) {
                 const int t = t0 + lane;
                 if (t < T) {
+                    if constexpr (NF == 1) cp_async8(&sct[warp][buf][lane][0], tp + t);
+                    else {
 #pragma unroll
-                    for (int k = 0; k < NF; k += 2) cp_async16(&sct[warp][buf][lane][k], tp + (int64_t)t * NF + k);
+                        for (int k = 0; k < NF; k += 2) cp_async16(&sct[warp][buf][lane][k], tp + (int64_t)t * NF + k);
+                    }
                 }
             }
         };
         if (doB) {
             if constexpr (kStageTab) { stage_tab(0, 0); cp_async_commit(); }
-            else if (T > 0) scn1 = __ldg(tp);
+            else if (NF == 1 && T > 0) scn1 = __ldg(tp);
 #pragma unroll
             for (int i = 0; i < kRing - 1; ++i) {               // rows 0 .. kRing-2 of the sequence to play: one group per row
                 if (i < T) {
@@ -508,10 +511,13 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     const double y = __hiloint2double(yhi, 0);
                     double scn[NF];
                     if constexpr (kStageTab) {
+                        if constexpr (NF == 1) scn[0] = lds_f64_v(sca);
+                        else {
 #pragma unroll
-                        for (int k = 0; k < NF; k += 2) {
-                            const double2 v = lds_v2f64_v(sca + k * 8);
-                            scn[k] = v.x; scn[k + 1] = v.y;
+                            for (int k = 0; k < NF; k += 2) {
+                                const double2 v = lds_v2f64_v(sca + k * 8);
+                                scn[k] = v.x; scn[k + 1] = v.y;
+                            }
                         }
                         sca += NF * 8;
                     } else {
@@ -529,20 +535,19 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                         cand[1] = cand[1] + fabs(z0 + y);
                         cand[2] = cand[2] + fabs(pw - y);
                         cand[3] = cand[3] + fabs(pw + y);
-                        if (NFTL > 0 && do_ftl) {
-                            // -(1/sqrt(th*th))*th with sqrt(fl(th*th)) == |th| and the branch-free reciprocal;
-                            // th == 0 plays -0.0 instead of 0.0 (z*x is a zero either way and df = -y exactly)
-                            const double n2 = th2l[0] * th2l[0];
-                            double rc = rcp_inrange(th2l[0]);           // garbage unless 1e-290 <= n2 <= 1e290
-                            const bool odd = !(n2 >= 1e-290 && n2 <= 1e290);
-                            if (odd) rc = (n2 == 0.0) ? 1.0 : 1.0 / sqrt(n2);
-                            const double x = -fabs(rc) * th2l[0];
+                        if constexpr (NFTL > 0) {
+                            // FTL action -(1/sqrt(th*th))*th = -th*|fl(1/th)| (sqrt(fl(th*th)) == |th|), branch-free and in the
+                            // same basic block as the FTRL variants below, so that its 12-deep dependent chain is scheduled
+                            // under them (computed even for items whose FTL columns are not written: do_ftl is only tested
+                            // at the end).  th is 0 or 2^-107 <= |th| <= T/2: every row of the g-path is 0 or a double of
+                            // magnitude >= 2^-54 (ziggurat: integer * wi[idx], clipped to [-1, 1]), hence a multiple of
+                            // 2^-106, and th = sum +-0.5 z.  So th*th neither under- nor overflows and rcp_inrange's range
+                            // holds unless th == 0, where the reference plays 0 (any zero: z*(+-0) - y == -y exactly).
+                            const double rc = rcp_inrange(th2l[0]);
+                            const double x = (th2l[0] == 0.0) ? 0.0 : -fabs(rc) * th2l[0];
                             const double df = z0 * x - y;
                             Sl = Sl + fabs(df);
-                            double g = gz;
-                            // (th*th under- or overflowed: |x| <= 1 is not guaranteed there, take the sign from df itself)
-                            if (odd) g = __hiloint2double(__double2hiint(hz0) ^ (__double2hiint(df) & 0x80000000), __double2loint(hz0));
-                            add_if_nonzero(th2l[0], df, g);                     // zero / NaN diff: no step (fast_algorithms.py:27-34)
+                            add_if_nonzero(th2l[0], df, gz);                    // zero / NaN diff: no step (fast_algorithms.py:27-34)
                         }
                         // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
                         // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     cp_async_commit();
                     slot = slot + kSlotBytes == kRingBytes ? 0u : slot + kSlotBytes;
                     slotn = slotn + kSlotBytes == kRingBytes ? 0u : slotn + kSlotBytes;
-                    if constexpr (NF == 1) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
+                    if constexpr (NF == 1 && !kStageTab) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
                 }
             }
         }

@@ -639,9 +639,12 @@ def main():
         fp64_peak = engine.fp64_peak_ops(local)
         kernel_steps_per_s = B * A * T * args.steps / (ms * 1e-3)           # this GPU's kernel rate
         alg_ops = (9 * d + 6)
-        kname = "sweep_kernel<GPathStream<%d>,%d,%d,%d>" % (
-            d, d, int(any(f != 0 for f in wl["alg"])),
+        # the kernel this workload launches (d = 1 g-path: the pipelined gsweep_kernel; profiles/r02_kernel_profiles.json)
+        kname = "gsweep_kernel<%d,%d,%d>" % (
+            d, int(any(f != 0 for f in wl["alg"])),
             (lambda n: 1 if n <= 1 else (4 if n <= 4 else 8))(sum(1 for f in wl["alg"] if f == 0)))
+        sm_count0 = torch.cuda.get_device_properties(local).multi_processor_count
+        ib0 = issue_bound(kname, sm_count0, (clocks or {}).get("sm_max_mhz"))
         line = {
             "metric": "trajectory-steps/sec", "value": value, "unit": "trajectory-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -661,6 +664,10 @@ def main():
                          "algorithmic_ops_per_trajectory_step": alg_ops,
                          "peak_source": "oco_fp64_peak_probe_host measured live (alternating DMUL/DADD, no FMA)",
                          "ncu": ncu_utilisation(kname),
+                         "issue_slot_bound": None if ib0 is None else {
+                             "steps_per_s_at_100pct_issue": ib0, "frac": kernel_steps_per_s / ib0,
+                             "note": "SMs x 4 schedulers x clock / warp-instructions per warp-step (committed ncu capture) x "
+                                     "32 lanes x trajectories per thread: the ceiling at the kernel's current instruction count"},
                          "hbm_view": hbm_view(ncu_traffic(kname, float(B) * A * T), ms / args.steps)},
             "result_check": {"max_regret_per_variant": [float(v) for v in st[:, 0]],
                              "mean_regret_per_variant": [float(v) for v in st[:, 1] / np.maximum(st[:, 3], 1)]},

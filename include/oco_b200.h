@@ -100,7 +100,7 @@ OCO_API int oco_simulate_batch_host(const void* z, const void* y, int in_dtype, 
                             double* theta_final, double* x_last, double* x_trace, int comparator_mode, int device);
 
 /* ---- exact_ftl.compute_prefix_actions + replay_exact_ftl (exact_ftl.py:280-333) for the unit
- * l2 ball, batched, d <= 8, in the LINEAR REGIME only (every row ||z_t||_2 <= 1, y_t = +-1;
+ * l2 ball, batched, d <= 256, in the LINEAR REGIME only (every row ||z_t||_2 <= 1, y_t = +-1;
  * there the SOCP of exact_ftl.py:83-105 has the closed-form minimiser v_k/||v_k||,
  * v_k = sum_{i<k} y_i z_i, and 0 on ties).  actions [B*(T+1)*d] (may be NULL), cum_loss /
  * comp_loss / regret [B] (may be NULL), status [B]: 0 = ok, 1 = some row is outside the regime
@@ -135,12 +135,14 @@ OCO_API int oco_exact_ftl_general_batch_host(const void* z, const void* y, int i
                                      double* regret, int* status, int device);
 
 /* ---- exact_ftl.replay_exact_ftl (exact_ftl.py:306-333) for caller-supplied actions [B*(T+1)*d]:
- * cum_loss = sum_t 0.5|z_t.actions[t] - y_t|, comp_loss = 0.5 sum_t |z_t.actions[T] - y_t|. d <= 8. */
+ * cum_loss = sum_t 0.5|z_t.actions[t] - y_t|, comp_loss = 0.5 sum_t |z_t.actions[T] - y_t|. d <= 256
+ * (bit-exact summation order for d <= 8, warp-parallel 1e-12 above). */
 OCO_API int oco_replay_actions_batch_host(const void* z, const void* y, int in_dtype, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum_loss, double* comp_loss, double* regret, int device);
 
 /* ---- fast_algorithms.simulate_SMART_like (fast_algorithms.py:184-195 -> :118-164), batched;
- * A <= OCO_MAX_SMART_THRESHOLDS (theta_thresh[a], eta0[a]) pairs per sequence, d <= 8.
+ * A <= OCO_MAX_SMART_THRESHOLDS (theta_thresh[a], eta0[a]) pairs per sequence, d <= 256 (d > 8: lane-distributed
+ * states, csrc/kernels_wide_smart.cu, 1e-12 class, both modes run the exact kernel with its pruning bound).
  * switch_t [B*A] (may be NULL) = step at which the switch test fired, -1 if never.
  * smart_mode 0: the reference's O(T^2) prefix-loss recomputation (:157-158), spread over a warp.
  * smart_mode 1: O(T) -- in the linear regime (||z_t|| <= 1, y_t = +-1) the leader's prefix loss is

@@ -377,7 +377,7 @@ OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t 
                     double* regret, int64_t* switch_t, int smart_mode, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, A)) return rc;
     if (A > OCO_MAX_SMART_THRESHOLDS) return fail(OCO_ERR_VALUE, "SMART: A <= %d thresholds per call (got %d)", OCO_MAX_SMART_THRESHOLDS, A);
-    if (d > kMaxSmallD) return fail(OCO_ERR_VALUE, "SMART: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > 256) return fail(OCO_ERR_VALUE, "SMART: d <= 256 supported (got %d)", d);
     if (!theta_thresh || !eta0 || (B > 0 && !regret)) return fail(OCO_ERR_VALUE, "theta_thresh / eta0 / regret must not be NULL");
     if (smart_mode != 0 && smart_mode != 1) return fail(OCO_ERR_VALUE, "unknown smart_mode %d", smart_mode);
     if (B == 0) return OCO_OK;
@@ -388,6 +388,12 @@ OCO_API int oco_smart_batch(const void* z, const void* y, int in_dtype, int64_t 
     CU(launch_ftrl_scale_table(tab.as<double>(), e, T, A, st));
     CU(th.alloc(sizeof(double) * A, st));
     CU(cudaMemcpyAsync(th.p, theta_thresh, sizeof(double) * A, cudaMemcpyHostToDevice, st));
+    if (d > kMaxSmallD) {
+        // 8 < d <= 256: warp per sequence with lane-distributed states (kernels_wide_smart.cu).  Both modes run the exact
+        // kernel: its pruning bound already makes sequences that stay away from their thresholds cost O(T d)
+        CU(launch_smart_wide(z, y, in_dtype == OCO_F32, B, T, d, th.as<double>(), tab.as<double>(), A, regret, switch_t, st));
+        return OCO_OK;
+    }
     DevBuf fl;
     if (smart_mode == 1) CU(fl.alloc(sizeof(int) * (size_t)B, st));
     CU(launch_smart(z, y, in_dtype == OCO_F32, B, T, d, th.as<double>(), tab.as<double>(), A, regret, switch_t, smart_mode,

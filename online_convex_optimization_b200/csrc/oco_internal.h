@@ -123,6 +123,11 @@ cudaError_t launch_smart(const void* z, const void* y, int in_f32, int64_t B, in
                          const double* thresh_dev, const double* scale_tab, int A,
                          double* regret, int64_t* switch_t, int mode, int* flags, cudaStream_t st);
 
+// SMART for 8 < d <= 256 (kernels_wide_smart.cu): lane-distributed states, exact pruning of the prefix loss, 1e-12 class
+cudaError_t launch_smart_wide(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
+                              const double* thresh_dev, const double* scale_tab, int A,
+                              double* regret, int64_t* switch_t, cudaStream_t st);
+
 // non-FMA fp64 issue-rate microbenchmark (16 ops per thread per iteration, 256 threads per block)
 cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t st);
 

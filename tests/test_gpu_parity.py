@@ -517,6 +517,36 @@ def test_smart_full_length_T1e4(eng):
     assert abs(fa.simulate_empirical_g_SMART(z[0], y[0], 15.0) - wr[0, 1]) <= REL * max(1.0, abs(wr[0, 1]))
 
 
+@pytest.mark.parametrize("d,T,B", [(10, 400, 9), (33, 300, 6), (64, 250, 5), (100, 120, 4), (256, 60, 3)])
+def test_smart_wide_d(eng, d, T, B):
+    """simulate_SMART_like for d > 8 (the reference has no limit on d; kernels_wide_smart.cu): regrets within 1e-12
+    and SWITCH TIMES against the oracle's literal O(T^2) loop -- g-path rows (unit ball: the pruning bound is
+    active) with thresholds that switch early / mid / never, the same rows scaled out of the ball with real-valued
+    labels (no pruning: every round takes the literal prefix loss), float32 inputs, and both modes."""
+    zs, ys = zip(*[O.gen_gpath(4, T, r, d) for r in range(B)])
+    z, y = np.stack(zs), np.stack(ys)
+    th, et = [1.5, 6.0, math.sqrt(2 * T), 1e9], [R2, 0.5 * R2, R2, R2]
+    wr, ws = O.smart_batch(z, y, th, et)
+    assert (ws[:, 0] >= 0).all() and (ws[:, 3] < 0).all()
+    for mode in ("exact", "linear"):
+        gr, gs = eng.smart_batch(z, y, th, et, mode=mode)
+        assert (gs == ws).all(), (mode, gs, ws)
+        assert np.all(np.abs(gr - wr) <= REL * np.maximum(1.0, np.abs(wr))), (mode, np.max(np.abs(gr - wr)))
+    z2 = z * 1.9; y2 = y * np.linspace(0.5, 1.5, T)[None, :]
+    wr2, ws2 = O.smart_batch(z2, y2, th, et)
+    gr2, gs2 = eng.smart_batch(z2, y2, th, et)
+    assert (gs2 == ws2).all()
+    assert np.all(np.abs(gr2 - wr2) <= REL * np.maximum(1.0, np.abs(wr2)))
+    z32, y32 = z.astype(np.float32), y.astype(np.float32)
+    wr3, ws3 = O.smart_batch(z32, y32, th[:2], et[:2])
+    gr3, gs3 = eng.smart_batch(z32, y32, th[:2], et[:2])
+    assert (gs3 == ws3).all() and np.all(np.abs(gr3 - wr3) <= REL * np.maximum(1.0, np.abs(wr3)))
+    # the drop-in single-sequence entry points
+    from online_convex_optimization_b200 import fast_algorithms as fa
+    assert abs(fa.simulate_SMART(z[0], y[0]) - wr[0, 2]) <= REL * max(1.0, abs(wr[0, 2]))
+    assert abs(fa.simulate_SMART_like(z[1], y[1], 6.0, 0.5 * R2) - wr[1, 1]) <= REL * max(1.0, abs(wr[1, 1]))
+
+
 def test_float32_mode_small_d_knife_edges(eng):
     """float32 mode against the reference's algorithms.py on d = 1 / 2 / 8 g-path rows cast to float32 (fixtures made by
     running the reference, tests/golden/driver32_stats.json): at d = 1 a third of the rows have |z| = 1 exactly and

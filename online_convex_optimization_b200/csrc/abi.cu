@@ -262,8 +262,10 @@ OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dty
                                 double* regret, int* status, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
     if (d > 256) return fail(OCO_ERR_VALUE, "exact FTL: d <= 256 supported (got %d)", d);
-    if (d > kMaxSmallD && norm != 0)
-        return fail(OCO_ERR_VALUE, "exact FTL on the linf / l1 ball: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > kMaxSmallD && norm == 2)
+        return fail(OCO_ERR_VALUE, "exact FTL on the l1 ball: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (d > kWideIpmMaxD && norm != 0)
+        return fail(OCO_ERR_VALUE, "exact FTL on the linf ball: d <= %d supported (got %d)", kWideIpmMaxD, d);
     if (norm < 0 || norm > 2) return fail(OCO_ERR_VALUE, "norm must be 0 (l2), 1 (linf) or 2 (l1)");
     if (max_iter < 1 || !(tol > 0.0)) return fail(OCO_ERR_VALUE, "need max_iter >= 1 and tol > 0");
     if (first_prefix < 0 || first_prefix > T + 1) return fail(OCO_ERR_VALUE, "need 0 <= first_prefix <= T + 1");
@@ -273,8 +275,24 @@ OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dty
     retain_pool_memory();
     DevBuf fl;
     const int* flagged = nullptr;
+    if (d > kMaxSmallD && d <= kWideIpmMaxD) {
+        // 8 < d <= 32: lane-per-variable interior-point kernel (kernels_wide_ipm.cu).  l2: the closed form wherever the
+        // sequence is in the linear regime (its status = 1 marks the others, which are then solved); linf: all solved
+        if (norm == 0) {
+            CU(launch_wide_exact_prefix(z, y, in_dtype == OCO_F32, B, T, d, actions, nullptr, nullptr, nullptr, status, st));
+            CU(fl.alloc(sizeof(int) * (size_t)B, st));
+            CU(cudaMemcpyAsync(fl.p, status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+            flagged = fl.as<int>();
+        }
+        CU(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, st));
+        CU(launch_exact_ftl_wide_general(z, y, in_dtype == OCO_F32, B, T, d, norm, max_iter, tol, first_prefix, flagged, actions,
+                                         status, st));
+        if (cum_loss || comp_loss || regret)
+            CU(launch_wide_replay(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, st));
+        return OCO_OK;
+    }
     if (d > kMaxSmallD) {
-        // l2 ball, d > 8: the closed form of the linear regime only (every reference workload); a sequence outside the
+        // l2 ball, d > 32: the closed form of the linear regime only (every reference workload); a sequence outside the
         // regime gets status T (= every prefix unsolved), which the shim turns into the reference's solver failure
         CU(launch_wide_exact_prefix(z, y, in_dtype == OCO_F32, B, T, d, actions, cum_loss, comp_loss, regret, status, st));
         CU(launch_status_scale(status, B, (int)std::min<int64_t>(T > 0 ? T : 1, 0x7fffffff), st));

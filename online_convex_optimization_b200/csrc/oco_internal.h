@@ -107,6 +107,11 @@ cudaError_t launch_sim_wide_tma(const void* z, const void* y, int in_f32, int64_
 cudaError_t launch_exact_ftl_general(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d, int norm,
                                      int max_iter, double tol, int64_t first_prefix, const int* only_flagged,
                                      double* actions, int* status, cudaStream_t st);
+// the same solver for 8 < d <= kWideIpmMaxD, l2 / linf balls (kernels_wide_ipm.cu: lane per variable, Hessian in shared memory)
+constexpr int kWideIpmMaxD = 32;
+cudaError_t launch_exact_ftl_wide_general(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d, int norm,
+                                          int max_iter, double tol, int64_t first_prefix, const int* only_flagged,
+                                          double* actions, int* status, cudaStream_t st);
 cudaError_t launch_replay_actions(const void* z, const void* y, int in_f32, int64_t B, int64_t T, int d,
                                   const double* actions, double* cum, double* comp, double* regret, cudaStream_t st);
 // 8 < d <= 256 twins of the three launchers above (kernels_wide_exact.cu: one warp per sequence / per (sequence, variant))

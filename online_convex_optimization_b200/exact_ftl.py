@@ -10,7 +10,9 @@ Two device solvers sit behind ``ExactFTLNoClip`` (DESIGN.md "Exact FTL"):
   d <= 256 (thread per sequence up to d = 8, warp per sequence beyond; the reference's own smoke run,
   exact_ftl.py:460-475, is d = 10 -- ``python -m online_convex_optimization_b200.exact_ftl`` runs it);
 * everything else (rows outside the ball, real-valued labels, the linf / l1 balls of
-  exact_ftl.py:91-96) with d <= 8: the interior-point solver of ``oco_exact_ftl_general_batch``,
+  exact_ftl.py:91-96) with d <= 32 (l1: d <= 8, its barrier has 2^d facets): the interior-point solver of
+  ``oco_exact_ftl_general_batch`` (per-lane registers up to d = 8, lane-per-variable with the Hessian in shared
+  memory beyond),
   duality gap <= ``solver_opts["tol"]`` * max(1, f(0)) (default 1e-8) within
   ``solver_opts["max_iter"]`` (default 300) Newton steps per prefix; a prefix that does not converge raises the
   ``RuntimeError`` exact_ftl.py:125-126 raises when its conic solver fails.
@@ -32,6 +34,9 @@ import numpy as np
 from . import engine
 
 
+GENERAL_MAX_D = 32      # oco_exact_ftl_general_batch: interior-point solver, l2 / linf balls (l1: d <= 8)
+
+
 def _ensure_float64_contiguous(arr: np.ndarray) -> np.ndarray:
     """exact_ftl.py:52-55."""
     if arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]:
@@ -47,9 +52,9 @@ def _solve_prefixes(z: np.ndarray, y: np.ndarray, *, norm: str = "l2", solver_op
         res = engine.exact_ftl_prefix_batch(z[None], y[None], want_actions=True)
         if int(res["status"][0]) == 0:
             return res
-    if z.shape[1] > 8:
+    if z.shape[1] > GENERAL_MAX_D:
         raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime "
-                           "(a row has ||z||_2 > 1 or a label is not +-1, and the general solver covers d <= 8)")
+                           f"(a row has ||z||_2 > 1 or a label is not +-1, and the general solver covers d <= {GENERAL_MAX_D})")
     res = engine.exact_ftl_general_batch(z[None], y[None], norm=norm, max_iter=int(opts.get("max_iter", 300)),
                                          tol=float(opts.get("tol", 1e-8)), first_prefix=z.shape[0] if only_last else 0)
     if int(res["status"][0]) != 0:
@@ -69,9 +74,9 @@ class ExactFTLNoClip:
         self.solver_opts = {} if solver_opts is None else dict(solver_opts)
         if self.norm not in ("l2", "linf", "l1"):
             raise ValueError("norm must be one of {'l2','linf','l1'}")
-        if self.norm != "l2" and self.d > 8:
+        if (self.norm == "l1" and self.d > 8) or (self.norm == "linf" and self.d > GENERAL_MAX_D):
             raise RuntimeError(f"Exact FTL (no clip) failed: status=unsupported_norm_{self.norm} "
-                               "(the linf / l1 solver covers d <= 8)")
+                               f"(the linf solver covers d <= {GENERAL_MAX_D}, the l1 solver d <= 8)")
         self._Z_buf = np.zeros((self.T_max, self.d), dtype=np.float64)
         self._y_buf = np.zeros(self.T_max, dtype=np.float64)
         self._w_buf = np.zeros(self.T_max, dtype=np.float64)

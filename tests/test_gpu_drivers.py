@@ -242,6 +242,53 @@ def test_exact_ftl_general_solver_vs_scipy(norm):
         assert (mixed["actions"][0].view(np.uint64) == O.exact_ftl_l2_prefix(zs, ys).view(np.uint64)).all()
 
 
+@pytest.mark.parametrize("norm,d", [("l2", 10), ("linf", 10), ("l2", 20), ("linf", 32), ("l2", 32)])
+def test_exact_ftl_general_solver_wide_d(norm, d):
+    """The general solver for 8 < d <= 32 (kernels_wide_ipm.cu: lane per variable, Hessian in shared memory) against
+    the scipy restatement of the reference's program: rows up to norm ~3, real-valued labels, prefixes shorter than d
+    (rank-deficient Hessians) and longer; includes the reference's own smoke shape (exact_ftl.py:460-475: d = 10)
+    pushed out of the linear regime.  Same bounds as the d <= 8 test."""
+    from online_convex_optimization_b200 import engine
+    from online_convex_optimization_b200 import exact_ftl as X
+    rng = np.random.default_rng(11 + d)
+    B, T = 3, 48
+    z = rng.standard_normal((B, T, d)) * (2.0 / np.sqrt(d))
+    y = rng.standard_normal((B, T))
+    res = engine.exact_ftl_general_batch(z, y, norm=norm)
+    assert (res["status"] == 0).all(), res["status"]
+    assert (res["actions"][:, 0] == 0).all()
+    pnorm = {"l2": 2, "linf": np.inf}[norm]
+    for b in range(B):
+        for k in (1, 3, d - 1, d + 1, 33, T):
+            x = res["actions"][b, k]
+            assert np.linalg.norm(x, pnorm) < 1.0
+            f, f_ref = _obj(x, z[b, :k], y[b, :k]), _scipy_opt(z[b, :k], y[b, :k], norm)
+            f0 = 0.5 * np.abs(y[b, :k]).sum()
+            assert f <= f_ref + (2e-6 if norm == "l2" else 2e-8) * max(1.0, f0), (norm, d, b, k, f, f_ref)
+        rep = O.replay_actions(z[b], y[b], res["actions"][b])
+        assert abs(res["regret"][b] - rep["regret"]) <= 1e-10 * max(1.0, abs(rep["regret"]))
+    last = engine.exact_ftl_general_batch(z, y, norm=norm, first_prefix=T)
+    assert (last["actions"][:, T].view(np.uint64) == res["actions"][:, T].view(np.uint64)).all()
+    starved = engine.exact_ftl_general_batch(z, y, norm=norm, max_iter=2)
+    assert (starved["status"] > 0).all()
+    if norm == "l2":     # sequences inside the linear regime keep the closed form; the others are solved
+        zs, ys = O.gen_gpath(4, 40, 1, d)
+        mixed = engine.exact_ftl_general_batch(np.stack([zs, zs * 3.0]), np.stack([ys, ys]))
+        assert (mixed["status"] == 0).all()
+        want = O.exact_ftl_l2_prefix(zs, ys)
+        assert np.all(np.abs(mixed["actions"][0] - want) <= 1e-12)
+        x3 = mixed["actions"][1, 40]
+        assert _obj(x3, zs * 3.0, ys) <= _scipy_opt(zs * 3.0, ys, "l2") + 2e-6 * 20
+        # the stateful twin (exact_ftl.py:130-193) on a sequence outside the regime
+        sol = X.ExactFTLNoClip(d=d, T_max=40)
+        xk = sol.solve_prefix_from_full(zs * 3.0, ys, 25)
+        assert _obj(xk, zs[:25] * 3.0, ys[:25]) <= _scipy_opt(zs[:25] * 3.0, ys[:25], "l2") + 2e-6 * 12.5
+    else:
+        sol = X.ExactFTLNoClip(d=d, T_max=T, norm="linf")
+        xk = sol.solve_prefix(z[0], y[0])
+        assert _obj(xk, z[0], y[0]) <= _scipy_opt(z[0], y[0], "linf") + 2e-8 * max(1.0, 0.5 * np.abs(y[0]).sum())
+
+
 # ------------------------------------------------------------------ exact_ftl.py deterministic half, reference-pinned
 def test_exact_ftl_twin_vs_reference_fixtures(golden_exact_det):
     """replay_exact_ftl / run_ftrl(comparator_action=...) / _simulate_ftrl of the twin against fixtures produced by

@@ -351,8 +351,16 @@ def test_exact_ftl_reference_smoke_configuration_d10():
     solver = X.ExactFTLNoClip(d=d, T_max=T)                      # stateful API at d = 10
     a1 = solver.append_row(z[0], float(y[0]))
     assert np.allclose(a1, actions[1]) and solver._last_length == 1
-    with pytest.raises(RuntimeError):                            # outside the linear regime at d > 8: solver failure
-        X.run_ftl_exact(z * 3.0, y)
+    # outside the linear regime: the general solver takes over up to d = 32 ...
+    res3, act3 = X.run_ftl_exact(z[:60] * 3.0, y[:60], return_actions=True)
+    for k in (5, 60):
+        val = 0.5 * np.abs(z[:k] * 3.0 @ act3[k] - y[:k]).sum()
+        ref = XS.solve(z[:k] * 3.0, y[:k], "l2")[0]
+        assert val <= ref + 2e-6 * max(1.0, 0.5 * k), (k, val, ref)
+    assert abs(res3.regret - (res3.cum_loss - res3.comp_loss)) < 1e-9
+    z40 = rng.normal(size=(30, 40))
+    with pytest.raises(RuntimeError):                            # ... beyond it: the reference's solver-failure exception
+        X.run_ftl_exact(z40, np.sign(rng.normal(size=30)))
 
 
 def test_driver_twin_vs_reference_driver_fixtures(golden_driver32):

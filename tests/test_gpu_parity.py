@@ -419,7 +419,8 @@ def _sweep_linear_check(eng, d, T, B, flags, etas, key_a, key_c0):
 
 
 @pytest.mark.parametrize("d,T,B,A", [(5, 300, 150, 1), (5, 201, 140, 2), (2, 100, 10, 4), (3, 257, 70, 9), (4, 64, 129, 5),
-                                     (5, 1, 3, 1), (5, 2, 1, 2), (2, 150, 70, 19), (8, 120, 131, 2), (7, 90, 40, 1), (6, 64, 33, 5)])
+                                     (5, 1, 3, 1), (5, 2, 1, 2), (2, 150, 70, 19), (8, 120, 131, 2), (7, 90, 40, 1), (6, 64, 33, 5),
+                                     (8, 70, 40, 12), (7, 65, 33, 9), (6, 97, 35, 10)])     # NF = 8: d = 7, 8 read the scale table directly
 def test_regret_sweep_linear_comparator(eng, d, T, B, A):
     flags = ([0, 1] + [0] * 7 + [1] + [0] * 9)[:A]
     etas = [R2 * s for s in (1.0, 1.0, 0.125, 0.25, 0.5, 2.0, 4.0, 8.0, 16.0, 1.0, .1, .2, .3, .4, .6, .7, .8, .9, 1.1)][:A]

@@ -235,17 +235,25 @@ __device__ __forceinline__ double lds_f64_v(uint32_t a) { double v; asm volatile
 __device__ __forceinline__ double2 lds_v2f64_v(uint32_t a) {
     double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v;
 }
-__device__ __forceinline__ bool zig_try_a(uint32_t tba, uint64_t r, double& x, int& idx, uint64_t& mag) {
-    idx = (int)(r & 0xff);
-    mag = ((r >> 9) & 0x000fffffffffffffULL) | 0x4330000000000000ULL;
-    const ulonglong2 wk = lds_v2u64(tba + (((uint32_t)r << 4) & 0xff0u));
+// `ki` receives the (pre-or'ed) threshold of the layer.  The fast test compares the HIGH words only: hi(mag) < hi(ki)
+// implies mag < ki, and the 2^-20 of the draws whose high words tie go to the slow path, which repeats the test on all
+// 64 bits first (zig_slow_la_a) -- same decisions, one instruction less on every draw.  `k52` is the exponent word
+// 0x43300000 held in a register so that mask-and-or is ONE LOP3 (two immediates would need two).
+__device__ __forceinline__ bool zig_try_a(uint32_t tba, uint32_t k52, uint64_t r, double& x, int& idx, uint64_t& mag, uint64_t& ki) {
+    idx = (int)((uint32_t)r & 0xffu);
+    const uint32_t mhi = (((uint32_t)(r >> 41)) & 0x000fffffu) | k52;
+    mag = ((uint64_t)mhi << 32) | (uint32_t)(r >> 9);
+    const ulonglong2 wk = lds_v2u64(tba + (uint32_t)idx * 16u);
     const int sgn = (int)(((uint32_t)r << 23) & 0x80000000u);                    // bit 8 of r -> sign bit
     const double w = __hiloint2double((int)(wk.x >> 32) ^ sgn, (int)(uint32_t)wk.x);   // (+-wi): (-a)*b == -(a*b)
     x = (__longlong_as_double((long long)mag) - 4503599627370496.0) * w;
-    return mag < wk.y;
+    ki = wk.y;
+    return mhi < (uint32_t)(wk.y >> 32);
 }
-static __device__ __forceinline__ double zig_slow_la_a(uint32_t tba, GenLA& g, const PcgInc& inc, int idx, uint64_t mag, double x) {
+static __device__ __forceinline__ double zig_slow_la_a(uint32_t tba, uint32_t k52, GenLA& g, const PcgInc& inc, int idx, uint64_t mag,
+                                                        uint64_t ki, double x) {
     for (;;) {
+        if (mag < ki) return x;                                // high words tied: the exact 64-bit fast test
         if (idx == 0) {
             const ZigTailLARet o = zig_tail_la(g.s.hi, g.s.lo, g.rn, inc.hi, inc.lo, mag & 0x000fffffffffffffULL);
             g.s.hi = o.hi; g.s.lo = o.lo; g.rn = o.rn;
@@ -260,19 +268,19 @@ static __device__ __forceinline__ double zig_slow_la_a(uint32_t tba, GenLA& g, c
         bool accept = sure_yes;
         if (!sure_yes && !sure_no) accept = zig_wedge_exact(yv, arg);
         if (accept) return x;
-        if (zig_try_a(tba, la_take(g, inc), x, idx, mag)) return x;     // rejected: a fresh attempt
+        if (zig_try_a(tba, k52, la_take(g, inc), x, idx, mag, ki)) return x;     // rejected: a fresh attempt
     }
 }
-__device__ __forceinline__ double zig_normal_la_a(uint32_t tba, GenLA& g, const PcgInc& inc) {
+__device__ __forceinline__ double zig_normal_la_a(uint32_t tba, uint32_t k52, GenLA& g, const PcgInc& inc) {
     const uint64_t r = la_take(g, inc);
-    double x; int idx; uint64_t mag;
-    if (zig_try_a(tba, r, x, idx, mag)) return x;
-    return zig_slow_la_a(tba, g, inc, idx, mag, x);
+    double x; int idx; uint64_t mag, ki;
+    if (zig_try_a(tba, k52, r, x, idx, mag, ki)) return x;
+    return zig_slow_la_a(tba, k52, g, inc, idx, mag, ki, x);
 }
 template <int D>
-__device__ __forceinline__ void gpath_row_la_a(uint32_t tba, GenLA& g, const PcgInc& inc, double (&z)[D]) {
+__device__ __forceinline__ void gpath_row_la_a(uint32_t tba, uint32_t k52, GenLA& g, const PcgInc& inc, double (&z)[D]) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) z[j] = zig_normal_la_a(tba, g, inc);
+    for (int j = 0; j < D; ++j) z[j] = zig_normal_la_a(tba, k52, g, inc);
     if constexpr (D == 1) {
         // z * fl(1/max(|z|, 1)): untouched unless |z| > 1 (z * 1.0 == z); sqrt(fl(z*z)) == |z| there, and
         // z * fl(1/|z|) == z * |fl(1/z)| (the reciprocal is odd); rcp_inrange's result is only used where 1 < |z| < 1e3
@@ -386,6 +394,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
     const int lane = tid & 31, warp = tid >> 5;
     // 32-bit shared-memory addresses, pinned in registers (see pin_u32)
     const uint32_t tba = pin_u32((uint32_t)__cvta_generic_to_shared(&tb));
+    const uint32_t k52 = pin_u32(0x43300000u);                  // exponent word of 2^52 (zig_try_a)
     const uint32_t ringa = pin_u32((uint32_t)__cvta_generic_to_shared(&ring[0][0][tid]));
     const uint32_t scta = pin_u32((uint32_t)__cvta_generic_to_shared(&sct[kStageTab ? warp : 0][0][0][0]));
     constexpr uint32_t kSlotBytes = D * kSweepBlock * 8, kRingBytes = kRing * kSlotBytes, kTabBufBytes = kTabBlock * NF * 8;
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
                 if (doA) {
                     double z[D];
-                    gpath_row_la_a<D>(tba, genA, incA, z);
+                    gpath_row_la_a<D>(tba, k52, genA, incA, z);
 #pragma unroll
                     for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
                     zw += D * kSweepBlock;
@@ -575,8 +584,10 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                                 } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
 #pragma unroll
                                     for (int k = 0; k < H; ++k) {
-                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: not used there
-                                        if (!(n2v[k] <= 1.0)) x1[k] = x1[k] * fac;
+                                        // (select on the FACTOR: the reciprocal chains of all variants stay in this basic block
+                                        //  and interleave; `if (need) x *= fac` let the compiler sink one chain under a branch)
+                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: replaced by 1.0
+                                        x1[k] = x1[k] * ((n2v[k] <= 1.0) ? 1.0 : fac);
                                     }
                                 }
                             }

@@ -1,5 +1,6 @@
-// gsweep_impl.cuh -- the g-path sweep for d > 1 with the single-pass ("linear") comparator:
-// generate + play + compare with NO second pass over the rows and the two phases software-pipelined.
+// gsweep_impl.cuh -- the fused g-path sweep (d = 1: exact candidate-sum comparator, bit-exact; 2 <= d <= 8: the
+// single-pass "linear" comparator): generate + play + compare with NO second pass over the rows and the two phases
+// software-pipelined.
 //
 //   gsweep_kernel<D, NFTL, NF>: one thread per seeded sequence of fast_algorithms.py:231-239
 //   (z = standard_normal((T, d)) clipped to the unit ball, y = choice([-1, 1], T)), persistent CTAs.
@@ -12,7 +13,8 @@
 //   at d = 5 -- the generator IS the cost (profiles/history/r02_gsweep_regen_experiment.md) -- so rows
 //   go through a per-CTA slab in HBM, laid out [t][j][thread] (every warp access one coalesced 256-B
 //   request).  What changed against sweep_kernel (sweep_impl.cuh):
-//     * no comparator pass (below): rows are read once, not twice, and no label words are stored;
+//     * no comparator pass (below): rows are read once, not twice; the labels are drawn by the generating side after
+//       the last row and parked 32 per word behind the rows (0.25 B per step), so the play side carries no generator;
 //     * the two phases of consecutive sequences are software-pipelined inside each thread: while
 //       row t of sequence k+1 is being generated (integer-ALU bound), row t of sequence k is loaded
 //       and played (HBM / fp64 bound) -- two independent dependency chains per thread and the slab

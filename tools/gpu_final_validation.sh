@@ -1,3 +1,5 @@
+# full GPU validation: pytest -m gpu, smoke, final ncu captures of the two sweep kernels and the launch list of the bench command.
+# usage: gpurun --timeout 1500 -- bash tools/gpu_final_validation.sh
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu 2>&1 | tail -4
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1

@@ -1,3 +1,5 @@
+# gsweep kernels on one B200: parity against the oracle (d = 1 bit-exact, d = 5 single-pass), timing vs the round-1 kernel, ncu instruction counts.
+# usage: gpurun -- bash tools/gpu_gsweep_check.sh
 mkdir -p gpurun_out
 python tools/try_c3.py parity 1000000 > gpurun_out/g_c3.log 2>&1
 python tools/try_gsweep.py parity time >> gpurun_out/g_c5.log 2>&1

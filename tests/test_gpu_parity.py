@@ -548,6 +548,34 @@ def test_smart_wide_d(eng, d, T, B):
     assert abs(fa.simulate_SMART_like(z[1], y[1], 6.0, 0.5 * R2) - wr[1, 1]) <= REL * max(1.0, abs(wr[1, 1]))
 
 
+def test_fused_sweep_random_shapes(eng):
+    """Randomised shapes of the fused g-path sweeps (tools/fuzz_gsweep.py, 24 cases): T around the 32-step blocks of the
+    packed labels / staged scale rows, B around the 128-sequence chunks, 1 ... 17 variants in 1 ... 3 groups with
+    random FTL columns and eta0, random stream keys.  d = 1 and the two-pass mode (d <= 5) bit-exact; the single-pass
+    mode within 1e-12 * max(1, cum_loss) with cum_loss bit-exact."""
+    rng = np.random.default_rng(2026)
+    bits = lambda a: np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+    for it in range(24):
+        d = int(rng.choice([1, 1, 2, 3, 4, 5, 5, 6, 7, 8]))
+        T = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 97, 128, 200, 513]))
+        B = int(rng.choice([1, 31, 32, 33, 127, 128, 129, 257, 700]))
+        A = int(rng.choice([1, 2, 3, 5, 8, 9, 12, 17]))
+        flags = [int(rng.random() < 0.25) for _ in range(A)]
+        etas = [float(R2 * 2.0 ** rng.integers(-4, 5) * (1.0 if rng.random() < 0.5 else rng.uniform(0.5, 1.5))) for _ in range(A)]
+        ka, kc = int(rng.integers(0, 5000)), int(rng.integers(0, 10 ** 6))
+        want = O.regret_sweep(ka, T, kc, B, d, flags, etas)
+        tag = (it, d, T, B, A)
+        if d <= 5:
+            got = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=ka, key_c0=kc, full=True)
+            assert (bits(got["regret"]) == bits(want)).all(), tag
+            assert got["stats"][:, 0].tolist() == want.max(axis=0).tolist(), tag
+        if d >= 2:
+            lin = eng.regret_sweep("gpath", B, T, d, flags, etas, key_a=ka, key_c0=kc, comparator="linear", full=True)
+            if d <= 5:
+                assert (bits(lin["cum_loss"]) == bits(got["cum_loss"])).all(), tag
+            assert np.all(np.abs(lin["regret"] - want) <= REL * np.maximum(1.0, lin["cum_loss"])), tag
+
+
 def test_float32_mode_small_d_knife_edges(eng):
     """float32 mode against the reference's algorithms.py on d = 1 / 2 / 8 g-path rows cast to float32 (fixtures made by
     running the reference, tests/golden/driver32_stats.json): at d = 1 a third of the rows have |z| = 1 exactly and

@@ -564,7 +564,10 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                         // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
                         // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
                         // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
-                        constexpr int H = NF >= 4 ? NF / 2 : NF;
+#ifndef OCO_GSWEEP_D1_GROUP
+#define OCO_GSWEEP_D1_GROUP 4               // variants handled together (tuning knob: 2 needs fewer temporaries, 4 gives more ILP)
+#endif
+                        constexpr int H = NF >= OCO_GSWEEP_D1_GROUP ? OCO_GSWEEP_D1_GROUP : NF;
 #pragma unroll
                         for (int h0 = 0; h0 < NF; h0 += H) {
                             double x1[H], n2v[H];

@@ -166,7 +166,7 @@ OCO_API int oco_gen_sequences_host(int family, uint64_t key_a, uint64_t key_c0, 
                            int64_t B, int64_t T, int d, double p_flip, int64_t block_len,
                            int out_dtype, void* z, void* y, int device);
 
-/* ---- fused generate + simulate + compare for seeded families GPATH / IID / NOISY, d <= 5:
+/* ---- fused generate + simulate + compare for seeded families GPATH (d <= 8) / IID / NOISY (d <= 5):
  * the sequences never exist in memory.  This is the inner double loop of
  * fast_algorithms.empirical_worst_case_thresholds (:226-243) and of
  * fast_driver.evaluate_stream_with_stats (:87-111, FTRL / FTL columns) as one launch.
@@ -181,7 +181,7 @@ OCO_API int oco_regret_sweep_host(int family, uint64_t key_a, uint64_t key_c0, c
                           const int* alg_flag, const double* eta0, int A,
                           double* regret, double* cum_loss, double* comp_loss, double* stats, int device);
 
-/* Same with an explicit comparator_mode (the entry points above are OCO_COMPARATOR_TWO_PASS, bit-exact for d <= 5):
+/* Same with an explicit comparator_mode (the entry points above are OCO_COMPARATOR_TWO_PASS, bit-exact):
  * OCO_COMPARATOR_LINEAR applies to the g-path family with 2 <= d <= 8 (d = 6, 7, 8 exist in this mode only; other
  * shapes ignore it and stay exact):
  * rows are regenerated in registers instead of being parked in a scratch slab (no DRAM traffic) and the
@@ -201,7 +201,7 @@ OCO_API int oco_regret_sweep_mode_host(int family, uint64_t key_a, uint64_t key_
 
 /* ---- fast_algorithms.empirical_worst_case_thresholds (fast_algorithms.py:211-247) for runs
  * [run_lo, run_lo + n_runs): g_max[i] = max(0, max_r regret_FTRL(eta0)) on g-path sequences of
- * length T_grid[i]; stats [nT*4] as above (may be NULL).  d <= 5 (the reference uses 5). */
+ * length T_grid[i]; stats [nT*4] as above (may be NULL).  d <= 8 (the reference uses 5). */
 OCO_API int oco_g_sweep_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,
                      int d, double eta0, double* g_max, double* stats, int device);
 OCO_API int oco_g_sweep_mode_host(const int64_t* T_grid, int nT, uint64_t run_lo, int64_t n_runs, uint64_t base_seed,

@@ -91,8 +91,8 @@ int check_family(int family, int d, bool fused, int comparator_mode = OCO_COMPAR
     if (family < OCO_FAM_GPATH || family > OCO_FAM_SWITCH) return fail(OCO_ERR_VALUE, "unknown sequence family %d", family);
     if (fused) {
         if (family > OCO_FAM_NOISY) return fail(OCO_ERR_VALUE, "fused sweep supports the seeded families only (got %d)", family);
-        const int dmax = (family == OCO_FAM_GPATH && comparator_mode == OCO_COMPARATOR_LINEAR) ? 8 : 5;   // gsweep_kernel: d <= 8
-        if (d > dmax) return fail(OCO_ERR_VALUE, "fused sweep supports d <= %d here (got %d; g-path with OCO_COMPARATOR_LINEAR: d <= 8); generate + simulate instead", dmax, d);
+        const int dmax = family == OCO_FAM_GPATH ? 8 : 5;      // theta of every variant lives in registers (thread per sequence)
+        if (d > dmax) return fail(OCO_ERR_VALUE, "fused sweep supports d <= %d here (got %d; g-path: d <= 8, iid families: d <= 5); generate + simulate instead", dmax, d);
     } else if (family == OCO_FAM_GPATH) {
         if (d > 128) return fail(OCO_ERR_VALUE, "g-path generator supports d <= 128 (got %d)", d);
     } else if (family <= OCO_FAM_NOISY) {

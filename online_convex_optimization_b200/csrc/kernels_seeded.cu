@@ -180,7 +180,7 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
         // (either mode, bit-exact); d >= 2 with OCO_COMPARATOR_LINEAR uses T/2 - ||theta_T|| (no second pass over the rows)
         return d <= 3 ? launch_gsweep_lo(a, d, st) : (d <= 5 ? launch_gsweep_hi(a, d, st) : launch_gsweep_wide(a, d, st));
     }
-    if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);
+    if (family == FAM_GPATH) return d <= 5 ? launch_sweep_gpath(a, d, st) : launch_sweep_gpath_wide(a, d, st);
     if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_iid(a, d, st);
     return cudaErrorInvalidValue;
 }

@@ -184,7 +184,7 @@ def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int
                  p_flip: float = -1.0, want_regret: bool = True, full: bool = False, comparator: str = "two_pass",
                  device: int = 0):
     """Fused generate+simulate+compare.  Returns dict(regret (B,A) | None, stats (A,4) = max,sum,sumsq,count
-    [, cum_loss, comp_loss]).  comparator="linear" (g-path, 2 <= d <= 5): no second pass, no scratch traffic,
+    [, cum_loss, comp_loss]).  comparator="linear" (g-path, 2 <= d <= 8): no second pass, no scratch traffic,
     regrets within 1e-12 * max(1, cum_loss) of the reference (see include/oco_b200.h)."""
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
     af, et = _variants(alg_flags, eta0s)

@@ -66,7 +66,9 @@ def test_argument_validation_is_value_error():
     assert rc == _lib.OCO_ERR_VALUE
     af = (ctypes.c_int * 1)(0)
     et = (ctypes.c_double * 1)(1.0)
-    rc = lib.oco_regret_sweep(0, 0, 0, None, 4, 10, 6, -1.0, af, et, 1, None, None, None, None, None)
+    rc = lib.oco_regret_sweep(0, 0, 0, None, 4, 10, 9, -1.0, af, et, 1, None, None, None, None, None)      # g-path: d <= 8
+    assert rc == _lib.OCO_ERR_VALUE and b"d <= 8" in lib.oco_last_error()
+    rc = lib.oco_regret_sweep(1, 0, 0, None, 4, 10, 6, -1.0, af, et, 1, None, None, None, None, None)      # iid family: d <= 5
     assert rc == _lib.OCO_ERR_VALUE and b"d <= 5" in lib.oco_last_error()
     rc = lib.oco_smart_batch(None, None, 1, 0, 4, 3, et, et, 9, None, None, 0, None)
     assert rc == _lib.OCO_ERR_VALUE

@@ -375,6 +375,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #endif
 constexpr int kLabelsPerWord = 32;          // packed labels: bit i of word w = 1 iff y[32 w + i] = -1
 constexpr int kTabBlock = 32;               // steps of the FTRL scale table staged at a time (one row per lane)
+static_assert(kTabBlock == kLabelsPerWord && kTabBlock == 32, "the step loop walks blocks of 32: one label word, one scale row per lane");
 
 // bytes of one slab (rows of one item, then its packed labels); two per resident CTA
 __host__ __device__ inline size_t gsweep_slab_bytes(int64_t T, int D) {

@@ -114,10 +114,10 @@ OCO_API int oco_exact_ftl_prefix_batch_host(const void* z, const void* y, int in
                                     int* status, int device);
 
 /* ---- general exact-FTL prefix solver: any rows / labels, unit ball norm 0 = l2, 1 = linf, 2 = l1
- * (exact_ftl.py:67-105 `norm=`), d <= 8.  For l2, sequences in the linear regime take the closed
+ * (exact_ftl.py:67-105 `norm=`), d <= 32 (l1: d <= 16).  For l2, sequences in the linear regime take the closed
  * form above; all others are solved, every prefix independently, by a path-following interior-point
  * method (Newton on the log-barrier function with the epigraph variables eliminated, see
- * csrc/kernels_exact.cu) until the duality gap is <= tol * max(1, f(0)), f(0) = 0.5*sum|y_i|
+ * csrc/kernels_exact.cu; d > 8: lane per variable, csrc/kernels_wide_ipm.cu) until the duality gap is <= tol * max(1, f(0)), f(0) = 0.5*sum|y_i|
  * (suggested tol 1e-8, what conic solvers deliver by default), using at most `max_iter` Newton steps
  * per prefix (suggested 300; 20-30 are typical).  status [B]: 0 = all prefixes converged, n > 0 =
  * n prefixes stopped at max_iter (treat like the reference's solver failure, exact_ftl.py:125-126).

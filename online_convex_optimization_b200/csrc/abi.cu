@@ -262,8 +262,8 @@ OCO_API int oco_exact_ftl_general_batch(const void* z, const void* y, int in_dty
                                 double* regret, int* status, void* stream) {
     if (int rc = check_common(z, y, in_dtype, B, T, d, 1)) return rc;
     if (d > 256) return fail(OCO_ERR_VALUE, "exact FTL: d <= 256 supported (got %d)", d);
-    if (d > kMaxSmallD && norm == 2)
-        return fail(OCO_ERR_VALUE, "exact FTL on the l1 ball: d <= %d supported (got %d)", kMaxSmallD, d);
+    if (2 * d > kWideIpmMaxD && norm == 2)
+        return fail(OCO_ERR_VALUE, "exact FTL on the l1 ball: d <= %d supported (got %d)", kWideIpmMaxD / 2, d);
     if (d > kWideIpmMaxD && norm != 0)
         return fail(OCO_ERR_VALUE, "exact FTL on the linf ball: d <= %d supported (got %d)", kWideIpmMaxD, d);
     if (norm < 0 || norm > 2) return fail(OCO_ERR_VALUE, "norm must be 0 (l2), 1 (linf) or 2 (l1)");

@@ -18,7 +18,9 @@
 //     below 1e-13 are dropped: at d = 32 the barrier of a nearly active bound makes the unscaled matrix span > 1e13);
 //     the two triangular solves run column by column with one shuffle per column;
 //   * the line search evaluates phi'(a) with lanes striding over the rows (x and the direction in shared memory).
-// The l1 ball has 2^d facets in this barrier and stays with the d <= 8 kernel.
+// The l1 ball (2^d facets in the d <= 8 kernel's barrier) is solved here in SPLIT VARIABLES for 8 < d <= 16:
+// x = u - w, u, w >= 0, sum(u + w) <= 1 -- 2d <= 32 variables (one per lane), 2d + 1 barrier terms, data rows [z, -z];
+// same Newton / line-search machinery, action = u - w.
 #include "oco_device.cuh"
 #include "oco_internal.h"
 
@@ -35,7 +37,7 @@ constexpr int kLineEvals = 12;
 struct WideIpmArgs {
     const void* z; const void* y;
     int64_t B, T; int d;
-    int norm;                 // 0 = l2, 1 = linf
+    int norm;                 // 0 = l2, 1 = linf, 2 = l1 (split variables, d <= 16)
     int max_iter; double tol;
     int64_t k0;
     const int* only_flagged;  // optional [B]
@@ -48,6 +50,11 @@ __device__ __forceinline__ double isum(double v) {
     for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
     return v;
 }
+__device__ __forceinline__ double imin(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
 __device__ __forceinline__ double imax(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -58,6 +65,7 @@ struct IpmSmem {
     double tile[32][kIpmLd];     // 32 staged rows (columns >= d are zero)
     double H[kIpmD][kIpmLd];     // Hessian / Cholesky factor (lower triangle)
     double x[kIpmD], dir[kIpmD], xa[kIpmD];
+    double xe[kIpmD], de[kIpmD];  // point / direction as seen by the data rows (l1: u - w; otherwise copies)
     double c[32], w[32];
 };
 
@@ -83,13 +91,15 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
     double sum_abs_y = 0.0;
     for (int64_t i = lane; i < k; i += 32) sum_abs_y += fabs((double)yb[i]);
     sum_abs_y = isum(sum_abs_y);
-    const double nu = p.norm == 0 ? 1.0 : 2.0 * d;
+    const bool split = p.norm == 2;                             // l1 ball: variables (u, w), x = u - w
+    const int nv = split ? 2 * d : d;                           // variables (one per lane)
+    const double nu = p.norm == 0 ? 1.0 : (split ? 2.0 * d + 1.0 : 2.0 * d);
     const double mu_f = p.tol * fmax(1.0, 0.5 * sum_abs_y) / ((double)k + nu);
     double mu = fmax(fmax(sum_abs_y / (double)k, mu_f), 1e-3);
 
-    const bool mine = lane < d;                                 // this lane owns a variable
-    double xv = 0.0;                                            // x[lane]
-    sm.x[lane] = 0.0; sm.dir[lane] = 0.0; sm.xa[lane] = 0.0;
+    const bool mine = lane < nv;                                // this lane owns a variable
+    double xv = (split && mine) ? 1.0 / (4.0 * d) : 0.0;        // x[lane]; l1: strictly feasible start, u - w = 0
+    sm.x[lane] = xv; sm.dir[lane] = 0.0; sm.xa[lane] = 0.0; sm.xe[lane] = 0.0; sm.de[lane] = 0.0;
 #pragma unroll 1
     for (int i = 0; i < 32; ++i) sm.tile[i][lane] = 0.0;
     __syncwarp();
@@ -101,10 +111,15 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
             const double n2 = isum(xl * xl), xp = isum(xl * dl);
             return 2.0 * mu * xp / (1.0 - n2);
         }
+        if (split) {                                            // -sum log v_a - log(1 - sum v)
+            const double sv = isum(xl), sd = isum(dl), a1 = isum(mine ? -dl / xl : 0.0);
+            return mu * (a1 + sd / (1.0 - sv));
+        }
         return isum(mine ? 2.0 * mu * xl * dl / (1.0 - xl * xl) : 0.0);
     };
     auto strictly_inside = [&](const double* xq) -> bool {
         const double xl = mine ? xq[lane] : 0.0;
+        if (split) return imin(mine ? xl : 1.0) > 1e-300 && isum(xl) < 1.0 - 1e-15;
         const double m = p.norm == 0 ? isum(xl * xl) : imax(fabs(xl));
         return m < 1.0 - 1e-15;
     };
@@ -122,13 +137,15 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
             __syncwarp();
             for (int e = lane; e < nrow * d; e += 32) {          // the tile's rows are one contiguous run: coalesced
                 const int ri = e / d, cj = e - ri * d;
-                sm.tile[ri][cj] = (double)zb[i0 * d + e];
+                const double zv = (double)zb[i0 * d + e];
+                sm.tile[ri][cj] = zv;
+                if (split) sm.tile[ri][d + cj] = -zv;           // data row of the split variables: [z, -z]
             }
             __syncwarp();
             double cw = 0.0, ww = 0.0;
             if (lane < nrow) {
                 double r = -(double)yb[i0 + lane];
-                for (int j = 0; j < d; ++j) r += sm.tile[lane][j] * sm.x[j];
+                for (int j = 0; j < nv; ++j) r += sm.tile[lane][j] * sm.x[j];
                 const double s = sqrt(mu2 + r * r), t = mu + s;
                 cw = r / t; ww = mu / (t * s);
             }
@@ -153,6 +170,13 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
 #pragma unroll
                 for (int j = 0; j < kIpmD; ++j) Hrow[j] += bq * xv * sm.x[j] + (j == lane ? a : 0.0);
             }
+        } else if (split) {
+            const double sl = 1.0 - isum(mine ? xv : 0.0), c1 = mu / sl, c2 = mu / (sl * sl);
+            if (mine) {
+                g += c1 - mu / xv;
+#pragma unroll
+                for (int j = 0; j < kIpmD; ++j) Hrow[j] += (j < nv ? c2 : 0.0) + (j == lane ? mu / (xv * xv) : 0.0);
+            }
         } else if (mine) {
             const double q = 1.0 - xv * xv;
             g += 2.0 * mu * xv / q;
@@ -173,7 +197,7 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < kIpmD; ++j)
-            sm.H[lane][j] = mine ? (j < d ? Hrow[j] * sc * sm.c[j] : 0.0) : (j == lane ? 1.0 : 0.0);
+            sm.H[lane][j] = mine ? (j < nv ? Hrow[j] * sc * sm.c[j] : 0.0) : (j == lane ? 1.0 : 0.0);
         __syncwarp();
         for (int j = 0; j < kIpmD; ++j) {                       // left-looking: lane i >= j forms column j
             double s = 0.0;
@@ -210,6 +234,8 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
         ++newton;
         sm.dir[lane] = dv;
         __syncwarp();
+        sm.de[lane] = split ? (lane < d ? dv - sm.dir[lane + d] : 0.0) : dv;
+        __syncwarp();
         // ---- step length: largest a <= 1 that stays strictly inside, then the root of phi'(a)
         double a = 1.0;
         for (int h = 0; h < 60; ++h) {
@@ -224,11 +250,13 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
             __syncwarp();
             sm.xa[lane] = xv + a * dv;
             __syncwarp();
+            sm.xe[lane] = split ? (lane < d ? sm.xa[lane] - sm.xa[lane + d] : 0.0) : sm.xa[lane];
+            __syncwarp();
             double da = 0.0;
             for (int64_t i = lane; i < k; i += 32) {
                 const TIN* __restrict__ zi = zb + i * d;
                 double r = -(double)yb[i], zp = 0.0;
-                for (int j = 0; j < d; ++j) { const double zj = (double)zi[j]; r += zj * sm.xa[j]; zp += zj * sm.dir[j]; }
+                for (int j = 0; j < d; ++j) { const double zj = (double)zi[j]; r += zj * sm.xe[j]; zp += zj * sm.de[j]; }
                 da += r / (mu + sqrt(mu2 + r * r)) * zp;
             }
             da = isum(da) + barrier_dir(sm.xa, sm.dir);
@@ -243,7 +271,8 @@ __global__ void __launch_bounds__(kIpmWarps * 32) exact_ftl_wide_barrier_kernel(
         __syncwarp();
     }
     if (!done && lane == 0) atomicAdd(p.status + b, 1);
-    if (mine) act[k * d + lane] = xv;
+    const double wv = __shfl_sync(0xffffffffu, xv, (lane + d) & 31);     // l1: the w half of the split variables
+    if (lane < d) act[k * d + lane] = split ? xv - wv : xv;
 }
 
 }  // namespace
@@ -253,7 +282,7 @@ cudaError_t launch_exact_ftl_wide_general(const void* z, const void* y, int in_f
                                           int max_iter, double tol, int64_t first_prefix, const int* only_flagged,
                                           double* actions, int* status, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    if (d < 1 || d > kIpmD || norm < 0 || norm > 1) return cudaErrorInvalidValue;
+    if (d < 1 || d > kIpmD || norm < 0 || norm > 2 || (norm == 2 && 2 * d > kIpmD)) return cudaErrorInvalidValue;
     if (T == 0) return cudaMemsetAsync(actions, 0, sizeof(double) * (size_t)B * d, st);
     WideIpmArgs a;
     a.z = z; a.y = y; a.B = B; a.T = T; a.d = d; a.norm = norm; a.max_iter = max_iter; a.tol = tol;

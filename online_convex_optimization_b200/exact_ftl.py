@@ -10,7 +10,7 @@ Two device solvers sit behind ``ExactFTLNoClip`` (DESIGN.md "Exact FTL"):
   d <= 256 (thread per sequence up to d = 8, warp per sequence beyond; the reference's own smoke run,
   exact_ftl.py:460-475, is d = 10 -- ``python -m online_convex_optimization_b200.exact_ftl`` runs it);
 * everything else (rows outside the ball, real-valued labels, the linf / l1 balls of
-  exact_ftl.py:91-96) with d <= 32 (l1: d <= 8, its barrier has 2^d facets): the interior-point solver of
+  exact_ftl.py:91-96) with d <= 32 (l1: d <= 16, split variables u - w beyond d = 8): the interior-point solver of
   ``oco_exact_ftl_general_batch`` (per-lane registers up to d = 8, lane-per-variable with the Hessian in shared
   memory beyond),
   duality gap <= ``solver_opts["tol"]`` * max(1, f(0)) (default 1e-8) within
@@ -34,7 +34,7 @@ import numpy as np
 from . import engine
 
 
-GENERAL_MAX_D = 32      # oco_exact_ftl_general_batch: interior-point solver, l2 / linf balls (l1: d <= 8)
+GENERAL_MAX_D = 32      # oco_exact_ftl_general_batch: interior-point solver, l2 / linf balls (l1: d <= 16)
 
 
 def _ensure_float64_contiguous(arr: np.ndarray) -> np.ndarray:
@@ -74,9 +74,9 @@ class ExactFTLNoClip:
         self.solver_opts = {} if solver_opts is None else dict(solver_opts)
         if self.norm not in ("l2", "linf", "l1"):
             raise ValueError("norm must be one of {'l2','linf','l1'}")
-        if (self.norm == "l1" and self.d > 8) or (self.norm == "linf" and self.d > GENERAL_MAX_D):
+        if (self.norm == "l1" and self.d > GENERAL_MAX_D // 2) or (self.norm == "linf" and self.d > GENERAL_MAX_D):
             raise RuntimeError(f"Exact FTL (no clip) failed: status=unsupported_norm_{self.norm} "
-                               f"(the linf solver covers d <= {GENERAL_MAX_D}, the l1 solver d <= 8)")
+                               f"(the linf solver covers d <= {GENERAL_MAX_D}, the l1 solver d <= {GENERAL_MAX_D // 2})")
         self._Z_buf = np.zeros((self.T_max, self.d), dtype=np.float64)
         self._y_buf = np.zeros(self.T_max, dtype=np.float64)
         self._w_buf = np.zeros(self.T_max, dtype=np.float64)

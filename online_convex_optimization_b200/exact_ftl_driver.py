@@ -61,8 +61,8 @@ def _exact_and_ftrl(z: np.ndarray, y: np.ndarray, *, norm: str = "l2", solver_op
         if ex["status"].any():
             ex = None
     if ex is None:
-        if z.shape[2] > 32 or (norm == "l1" and z.shape[2] > 8):
-            raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime (general solver covers d <= 32; l1: d <= 8)")
+        if z.shape[2] > 32 or (norm == "l1" and z.shape[2] > 16):
+            raise RuntimeError("Exact FTL (no clip) failed: status=outside_linear_regime (general solver covers d <= 32; l1: d <= 16)")
         ex = engine.exact_ftl_general_batch(z, y, norm=norm, tol=float(opts.get("tol", 1e-8)), max_iter=int(opts.get("max_iter", 300)),
                                             first_prefix=z.shape[1] if only_comparator else 0)
         if ex["status"].any():

@@ -132,7 +132,7 @@ def test_exact_ftl_twin_api_and_known_answers():
     with pytest.raises(RuntimeError):                                 # a solve that cannot converge reports failure
         ex.compute_prefix_actions(ex.ExactFTLNoClip(d=3, T_max=40, solver_opts={"max_iter": 2}), z * 5.0, y)
     with pytest.raises(RuntimeError):
-        ex.ExactFTLNoClip(d=9, T_max=4, norm="l1")
+        ex.ExactFTLNoClip(d=17, T_max=4, norm="l1")
     # run_ftrl with the exact comparator == oracle FTRL play + comparator loss at the exact action
     r = ex.run_ftrl(z, y, eta0=R2, comparator_action=acts[-1])
     o = O.simulate_alg(z, y, 0, R2, trace=True)
@@ -242,10 +242,10 @@ def test_exact_ftl_general_solver_vs_scipy(norm):
         assert (mixed["actions"][0].view(np.uint64) == O.exact_ftl_l2_prefix(zs, ys).view(np.uint64)).all()
 
 
-@pytest.mark.parametrize("norm,d", [("l2", 10), ("linf", 10), ("l2", 20), ("linf", 32), ("l2", 32)])
+@pytest.mark.parametrize("norm,d", [("l2", 10), ("linf", 10), ("l2", 20), ("linf", 32), ("l2", 32), ("l1", 10), ("l1", 16)])
 def test_exact_ftl_general_solver_wide_d(norm, d):
     """The general solver for 8 < d <= 32 (kernels_wide_ipm.cu: lane per variable, Hessian in shared memory) against
-    the scipy restatement of the reference's program: rows up to norm ~3, real-valued labels, prefixes shorter than d
+    the scipy restatement of the reference's program (l2, linf; l1 in split variables up to d = 16): rows up to norm ~3, real-valued labels, prefixes shorter than d
     (rank-deficient Hessians) and longer; includes the reference's own smoke shape (exact_ftl.py:460-475: d = 10)
     pushed out of the linear regime.  Same bounds as the d <= 8 test."""
     from online_convex_optimization_b200 import engine
@@ -257,7 +257,7 @@ def test_exact_ftl_general_solver_wide_d(norm, d):
     res = engine.exact_ftl_general_batch(z, y, norm=norm)
     assert (res["status"] == 0).all(), res["status"]
     assert (res["actions"][:, 0] == 0).all()
-    pnorm = {"l2": 2, "linf": np.inf}[norm]
+    pnorm = {"l2": 2, "linf": np.inf, "l1": 1}[norm]
     for b in range(B):
         for k in (1, 3, d - 1, d + 1, 33, T):
             x = res["actions"][b, k]
@@ -284,9 +284,12 @@ def test_exact_ftl_general_solver_wide_d(norm, d):
         xk = sol.solve_prefix_from_full(zs * 3.0, ys, 25)
         assert _obj(xk, zs[:25] * 3.0, ys[:25]) <= _scipy_opt(zs[:25] * 3.0, ys[:25], "l2") + 2e-6 * 12.5
     else:
-        sol = X.ExactFTLNoClip(d=d, T_max=T, norm="linf")
+        sol = X.ExactFTLNoClip(d=d, T_max=T, norm=norm)
         xk = sol.solve_prefix(z[0], y[0])
-        assert _obj(xk, z[0], y[0]) <= _scipy_opt(z[0], y[0], "linf") + 2e-8 * max(1.0, 0.5 * np.abs(y[0]).sum())
+        assert _obj(xk, z[0], y[0]) <= _scipy_opt(z[0], y[0], norm) + 2e-8 * max(1.0, 0.5 * np.abs(y[0]).sum())
+    if norm == "l1":     # split variables (x = u - w) cover the l1 ball up to d = 16; beyond: the reference's solver-failure exception
+        with pytest.raises(RuntimeError):
+            X.ExactFTLNoClip(d=17, T_max=4, norm="l1")
 
 
 # ------------------------------------------------------------------ exact_ftl.py deterministic half, reference-pinned

@@ -29,13 +29,15 @@ def allreduce_stats(stats, group=None):
         return stats
     world = dist.get_world_size(group)
     mine = stats.contiguous()
+    if mine.is_cuda and dist.get_backend(group) == "gloo":
+        mine = mine.cpu()           # several ranks sharing one GPU (tests on a 1-GPU box): gloo moves host tensors
     allst = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allst, mine, group=group)
     out = allst[0].clone()
     for r in range(1, world):                       # fixed order: deterministic sums
         out[..., 0] = torch.maximum(out[..., 0], allst[r][..., 0])
         out[..., 1:] = out[..., 1:] + allst[r][..., 1:]
-    stats.copy_(out)
+    stats.copy_(out)             # (host -> device when the collective ran on host copies)
     return stats
 
 

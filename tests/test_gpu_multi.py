@@ -1,5 +1,7 @@
-"""Multi-GPU test (-m gpu, needs >= 2 visible GPUs; skipped otherwise): a g(T)-style sweep sharded over
-2 ranks with NCCL gives the single-GPU statistics -- MAX bit-identical, SUM within 1e-14."""
+"""Multi-rank tests (-m gpu): a g(T)-style sweep sharded over 2 ranks gives the single-GPU statistics -- MAX
+bit-identical, SUM within 1e-14.  With >= 2 visible GPUs the ranks use one GPU each and NCCL; on a
+1-GPU box the same sharding logic runs with both ranks on cuda:0 and the one collective over gloo (host copies of the
+few hundred bytes of statistics), so the sharded path has a test on every box."""
 import math
 import os
 
@@ -13,11 +15,15 @@ pytestmark = pytest.mark.gpu
 R2 = math.sqrt(2.0)
 
 
-def _worker(rank, world, port, n_runs, T, q):
+def _worker(rank, world, port, n_runs, T, q, backend="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     from online_convex_optimization_b200 import dist as odist
     reg, stats = odist.regret_sweep_sharded("gpath", n_runs, T, 5, [0, 1], [R2, R2], key_a=0, run_lo=0, want_regret=True)
     g = {}
@@ -29,15 +35,18 @@ def _worker(rank, world, port, n_runs, T, q):
     dist.destroy_process_group()
 
 
-def test_sharded_sweep_equals_single_gpu():
-    if torch.cuda.device_count() < 2:
+@pytest.mark.parametrize("backend", ["nccl", "gloo_one_gpu"])
+def test_sharded_sweep_equals_single_gpu(backend):
+    if backend == "nccl" and torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
     from online_convex_optimization_b200 import engine
     n_runs, T, world = 1001, 300, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_runs, T, q)) for r in range(world)]
+    port = 29600 + (os.getpid() % 1000) + (0 if backend == "nccl" else 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_runs, T, q, "nccl" if backend == "nccl" else "gloo")) for r in range(world)]
     for p in procs:
         p.start()
     got = {}

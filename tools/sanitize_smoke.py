@@ -31,3 +31,15 @@ a10 = engine.simulate_batch(z10, y10, [0, 1], [R2, R2], full=True, comparator_ac
 zf, yf = engine.gen_sequences("gpath", 70, 48, 5, dtype=np.float32)
 a32 = engine.simulate_batch(zf, yf, [0, 1, 0, 0, 1], [R2, R2, 0.1, 3.0, 1.0], compute="f32", full=True)
 print("sanitize smoke done", float(r["stats"][0, 0]), float(w[0, 0]))
+# last session of round 2: packed labels / staged scale rows at ragged T (31, 33, 65), NF = 4 / 8 at d = 1 ... 8, the two-pass
+# fused sweep at d = 6 ... 8, SMART for d > 8, the lane-per-variable interior-point kernel (l2 / linf / l1 split variables)
+for d_, T_, A_ in ((1, 31, 9), (1, 65, 5), (2, 33, 9), (5, 97, 12), (6, 33, 5), (7, 40, 9), (8, 35, 2)):
+    fl = ([0, 1] + [0] * 15)[:A_]; et = [R2 * (0.25 + 0.5 * i) for i in range(A_)]
+    r = engine.regret_sweep("gpath", 257, T_, d_, fl, et, full=True)
+    if d_ >= 2:
+        r = engine.regret_sweep("gpath", 257, T_, d_, fl, et, comparator="linear", full=True)
+z12, y12 = engine.gen_sequences("gpath", 5, 60, 12); z70, y70 = engine.gen_sequences("gpath", 3, 41, 70)
+s = engine.smart_batch(z12, y12, [1.5, 6.0, 1e9], [R2, R2, R2]); s = engine.smart_batch(z70 * 1.7, y70, [2.0], [R2])
+for nm, zz in (("l2", z12 * 3.0), ("linf", z12 * 2.0), ("l1", z12 * 2.0)):
+    ge = engine.exact_ftl_general_batch(zz[:, :23].copy(), y12[:, :23].copy(), norm=nm)
+print("sanitize smoke (round 2, last session) done", int(ge["status"].sum()))

@@ -191,43 +191,8 @@ static __device__ __noinline__ ZigTailLARet zig_tail_la(uint64_t s_hi, uint64_t 
         }
     }
 }
-static __device__ __forceinline__ double zig_slow_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc, int idx, uint64_t mag, double x) {
-    for (;;) {
-        if (idx == 0) {
-            const ZigTailLARet o = zig_tail_la(g.s.hi, g.s.lo, g.rn, inc.hi, inc.lo, mag & 0x000fffffffffffffULL);
-            g.s.hi = o.hi; g.s.lo = o.lo; g.rn = o.rn;
-            return o.x;
-        }
-        const double f1 = tb.fi[idx], f0 = tb.fi[idx - 1];
-        const double yv = (f0 - f1) * la_double(g, inc) + f1;
-        const double arg = -0.5 * x * x;
-        const double ef = (double)__expf((float)arg);
-        const bool sure_yes = yv < ef * (1.0 - 1e-5), sure_no = yv > ef * (1.0 + 1e-5);
-        bool accept = sure_yes;
-        if (!sure_yes && !sure_no) accept = zig_wedge_exact(yv, arg);
-        if (accept) return x;
-        if (zig_try(tb, la_take(g, inc), x, idx, mag)) return x;     // rejected: a fresh attempt
-    }
-}
-__device__ __forceinline__ double zig_normal_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc) {
-    const uint64_t r = la_take(g, inc);
-    double x; int idx; uint64_t mag;
-    if (zig_try(tb, r, x, idx, mag)) return x;
-    return zig_slow_la(tb, g, inc, idx, mag, x);
-}
-template <int D>
-__device__ __forceinline__ void gpath_row_la(const ZigTab2& tb, GenLA& g, const PcgInc& inc, double (&z)[D]) {
-#pragma unroll
-    for (int j = 0; j < D; ++j) z[j] = zig_normal_la(tb, g, inc);
-    double nrm;
-    if constexpr (D == 1) nrm = fabs(z[0]);     // sqrt(fl(z*z)) == |z| for 1 < |z| < 1e145, and both are <= 1 together otherwise
-    else nrm = sqrt_of_sumsq<D>(np_pairwise_sumsq<D, double>(z), z[0]);
-    const double inv = rcp_inrange(nrm > 1.0 ? nrm : 1.0);      // 1 <= norm < 1e3
-#pragma unroll
-    for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
-}
-// ---- the same generator reading the tables through a PINNED 32-bit shared-memory address: ptxas otherwise
-// rematerialises the shared-window base of a static __shared__ object (S2UR SR_CgaCtaId + UMOV + ULEA) at every use
+// ---- ziggurat with the lookahead stream, reading the tables through a PINNED 32-bit shared-memory address: ptxas
+// otherwise rematerialises the shared-window base of a static __shared__ object (S2UR SR_CgaCtaId + UMOV + ULEA) at every use
 __device__ __forceinline__ uint32_t pin_u32(uint32_t v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
 __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
     ulonglong2 v; asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a)); return v;
@@ -295,18 +260,6 @@ __device__ __forceinline__ void gpath_row_la_a(uint32_t tba, uint32_t k52, GenLA
         for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
     }
 }
-// Generator.choice([-1.0, 1.0], size=T) continuing a lookahead stream: one 32-bit draw per label, low half of
-// each raw first, then the high half; label = top bit (rng_numpy.cuh::LabelCursor with the raw prefetched)
-struct LabelCursorLA {
-    GenLA g; uint64_t cur;
-    __device__ __forceinline__ double next(int t, const PcgInc& inc) {
-        uint32_t w;
-        if ((t & 1) == 0) { cur = la_take(g, inc); w = (uint32_t)cur; }
-        else w = (uint32_t)(cur >> 32);
-        return (w >> 31) ? 1.0 : -1.0;
-    }
-};
-
 // ---------------------------------------------------------------- exact fallback (never taken on g-path data)
 // Literal second pass sum_t |z_t.a - y_t| for one sequence and one comparator a (fast_algorithms.py:69-76):
 // count pass for the label cursor, then regenerate rows and labels.

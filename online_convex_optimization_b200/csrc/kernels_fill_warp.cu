@@ -38,7 +38,7 @@ struct WarpGenArgs {
 };
 
 // wedge acceptance for candidate (x, idx) with the uniform drawn from raw r -- the same decision procedure as
-// zig_slow_la (float bracket, exact exp only inside the +-1e-5 band)
+// zig_slow_la_a (float bracket, exact exp only inside the +-1e-5 band)
 __device__ __forceinline__ bool wedge_accept(const ZigTab2& tb, double x, int idx, uint64_t r) {
     const double u = __ull2double_rn(r >> 11) * (1.0 / 9007199254740992.0);
     const double f1 = tb.fi[idx], f0 = tb.fi[idx - 1];

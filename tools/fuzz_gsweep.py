@@ -12,8 +12,8 @@ bits = lambda a: np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 bad = 0
 for it in range(n):
     d = int(rng.choice([1, 1, 2, 3, 4, 5, 5, 6, 7, 8]))
-    T = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 97, 128, 200, 513, 1000]))
-    B = int(rng.choice([1, 31, 32, 33, 127, 128, 129, 257, 700]))
+    T = int(rng.choice([1, 2, 31, 32, 33, 63, 64, 65, 97, 128, 200, 513, 1000, 4097, 10000]))
+    B = int(rng.choice([1, 31, 32, 33, 127, 128, 129, 257, 700] if T < 4000 else [5, 130, 300]))
     A = int(rng.choice([1, 2, 3, 5, 8, 9, 12, 17]))
     flags = [int(rng.random() < 0.25) for _ in range(A)]
     etas = [float(math.sqrt(2.0) * 2.0 ** rng.integers(-4, 5) * (1.0 if rng.random() < 0.5 else rng.uniform(0.5, 1.5))) for _ in range(A)]

@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "liboco_b200.so")
-SOURCES = ["abi.cu", "kernels_seeded.cu", "kernels_sweep_gpath.cu", "kernels_sweep_gpath_wide.cu", "kernels_sweep_iid.cu", "kernels_gsweep_lo.cu", "kernels_gsweep_hi.cu", "kernels_gsweep_wide.cu", "kernels_stream.cu", "kernels_warp.cu", "kernels_wide_tma.cu", "kernels_exact.cu", "kernels_wide_exact.cu", "kernels_fill_warp.cu", "kernels_wide_smart.cu", "kernels_wide_ipm.cu"]
+SOURCES = ["abi.cu", "kernels_seeded.cu", "kernels_sweep_gpath.cu", "kernels_sweep_iid.cu", "kernels_gsweep_lo.cu", "kernels_gsweep_hi.cu", "kernels_gsweep_wide.cu", "kernels_stream.cu", "kernels_warp.cu", "kernels_wide_tma.cu", "kernels_exact.cu", "kernels_wide_exact.cu", "kernels_fill_warp.cu", "kernels_wide_smart.cu", "kernels_wide_ipm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",

@@ -260,26 +260,42 @@ __device__ __forceinline__ void gpath_row_la_a(uint32_t tba, uint32_t k52, GenLA
         for (int j = 0; j < D; ++j) z[j] = z[j] * inv;
     }
 }
-// ---------------------------------------------------------------- exact fallback (never taken on g-path data)
-// Literal second pass sum_t |z_t.a - y_t| for one sequence and one comparator a (fast_algorithms.py:69-76):
-// count pass for the label cursor, then regenerate rows and labels.
+// ---------------------------------------------------------------- literal comparator pass
+// sum_t |z_t.a - y_t| for one sequence and one comparator a, in the reference's order (fast_algorithms.py:69-76), over the
+// rows and packed labels of the item just played: they are still in the slab (the generating side overwrites it only
+// in the next round).  Taken by every trajectory in the two-pass comparator mode (bit-exact regrets for any d <= 8), by
+// the test hook OCO_SWEEP_FORCE_SECOND_PASS, and by a sequence whose single-pass check failed (never observed).
+// Four rows are requested before the first is consumed (thread-private columns: every warp access is coalesced).
 template <int D>
-static __device__ __noinline__ double gsweep_exact_comp(const ZigTab2* tbp, uint64_t ka, int T, uint64_t kc, const double* a_in) {
-    const ZigTab2& tb = *tbp;
+static __device__ __noinline__ double gsweep_slab_comp(const double* __restrict__ zr, const uint32_t* __restrict__ lr, int T,
+                                                        const double* __restrict__ a_in) {
     double a[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) a[j] = a_in[j];
-    Pcg64 s; PcgInc inc;
-    pcg_seed3(s, inc, ka, (uint64_t)T, kc);
-    Pcg64 s0 = s;
-    for (int64_t n = 0; n < (int64_t)T * D; ++n) zig_skip2(tb, s, inc);
-    LabelCursor lab; lab.s = s; lab.cur = 0;
-    s = s0;
     double C = 0.0;
-    for (int t = 0; t < T; ++t) {
+    uint32_t lw = 0;
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {
+        if ((t & 31) == 0) lw = __ldcg(lr + (int64_t)(t >> 5) * kSweepBlock);
+        double z[4][D];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) z[i][j] = __ldcg(zr + ((int64_t)(t + i) * D + j) * kSweepBlock);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double y = __hiloint2double((int)((lw << 31) | 0x3ff00000u), 0);
+            lw >>= 1;
+            C = C + fabs(dot_seq<D>(z[i], a) - y);
+        }
+    }
+    for (; t < T; ++t) {
+        if ((t & 31) == 0) lw = __ldcg(lr + (int64_t)(t >> 5) * kSweepBlock);
         double z[D];
-        gpath_row2<D>(tb, s, inc, z);
-        const double y = lab.next(t, inc);
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = __ldcg(zr + ((int64_t)t * D + j) * kSweepBlock);
+        const double y = __hiloint2double((int)((lw << 31) | 0x3ff00000u), 0);
+        lw >>= 1;
         C = C + fabs(dot_seq<D>(z, a) - y);
     }
     return C;
@@ -644,17 +660,18 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     else if (a1[0] == kW) C = cand[2]; else if (a1[0] == -kW) C = cand[3];
                     else if (a1[0] == 0.0) C = (double)T; else found = false;   // not reachable for finite theta
                     if (found && !p.force_second_pass) { comp = 0.5 * C; reg = cum - comp; return; }
-                } else if (ok < 0 && !zero_df && !p.force_second_pass) {
+                } else if (ok < 0 && !zero_df && !p.force_second_pass && !p.literal) {
                     comp = halfT - nth;
                     reg = (cum - halfT) + nth;
                     return;
                 }
-                {                                               // literal second pass (exact)
+                {                                               // literal second pass over the slab (exact)
                     double a[D];
                     ftl_action<D>(th2, a);
-                    const uint64_t ka = p.keys ? p.keys[2 * bB] : p.key_a;
-                    const uint64_t kc = p.keys ? p.keys[2 * bB + 1] : p.key_c0 + (uint64_t)bB;
-                    comp = 0.5 * gsweep_exact_comp<D>(&tb, ka, T, kc, a);
+                    // (the slab pointers are recomputed here: keeping zr / lr alive across the step loop costs registers there)
+                    const char* const sR = slab_base + (size_t)((r + 1) & 1) * slab_bytes;
+                    comp = 0.5 * gsweep_slab_comp<D>(reinterpret_cast<const double*>(sR) + tid,
+                                                     reinterpret_cast<const uint32_t*>(sR + row_bytes) + tid, T, a);
                     reg = cum - comp;
                 }
             };

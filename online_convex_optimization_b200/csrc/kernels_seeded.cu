@@ -174,13 +174,17 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
     }
     a.debug_phase = 0;
     if (const char* e = getenv("OCO_GSWEEP_DEBUG")) a.debug_phase = atoi(e);     // timing experiments: one phase only
-    const char* legacy = getenv("OCO_SWEEP_D1_LEGACY");                          // A/B knob: round-1 kernel for d = 1
-    if (family == FAM_GPATH && ((d == 1 && !(legacy && legacy[0] == '1')) || (d >= 2 && comparator_mode == 1))) {
-        // software-pipelined generate / play kernel (gsweep_impl.cuh): d = 1 keeps the exact candidate-sum comparator
-        // (either mode, bit-exact); d >= 2 with OCO_COMPARATOR_LINEAR uses T/2 - ||theta_T|| (no second pass over the rows)
+    a.literal = comparator_mode == 1 ? 0 : 1;
+    const char* legacy = getenv("OCO_SWEEP_LEGACY");                             // A/B knob: the round-1 three-phase kernel (d <= 5)
+    if (!legacy) legacy = getenv("OCO_SWEEP_D1_LEGACY");
+    const bool use_legacy = legacy && legacy[0] == '1' && d <= 5;
+    if (family == FAM_GPATH && !use_legacy) {
+        // software-pipelined generate / play kernel (gsweep_impl.cuh), any d <= 8: d = 1 keeps the exact candidate-sum
+        // comparator (either mode, bit-exact); d >= 2: OCO_COMPARATOR_LINEAR uses T/2 - ||theta_T|| (no second pass over
+        // the rows), the two-pass mode re-reads the item's rows from the slab for the literal comparator loss (bit-exact)
         return d <= 3 ? launch_gsweep_lo(a, d, st) : (d <= 5 ? launch_gsweep_hi(a, d, st) : launch_gsweep_wide(a, d, st));
     }
-    if (family == FAM_GPATH) return d <= 5 ? launch_sweep_gpath(a, d, st) : launch_sweep_gpath_wide(a, d, st);
+    if (family == FAM_GPATH) return launch_sweep_gpath(a, d, st);
     if (family == FAM_IID || family == FAM_NOISY) return launch_sweep_iid(a, d, st);
     return cudaErrorInvalidValue;
 }

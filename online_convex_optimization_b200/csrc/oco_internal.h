@@ -56,8 +56,7 @@ cudaError_t launch_sweep_table(double* tab, const SweepPlan& plan, int64_t T, cu
 cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint64_t* keys, int64_t T, int64_t B, int d,
                          double p_flip, const SweepPlan& plan, const double* sweep_tab,
                          double* regret, double* cum, double* comp, double* partials, int comparator_mode, cudaStream_t st);
-cudaError_t launch_sweep_gpath(const struct SweepArgs& a, int d, cudaStream_t st);        // d = 1 .. 5
-cudaError_t launch_sweep_gpath_wide(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 6, 7, 8
+cudaError_t launch_sweep_gpath(const struct SweepArgs& a, int d, cudaStream_t st);        // round-1 kernel, d = 1 .. 5 (OCO_SWEEP_LEGACY=1)
 // g-path, 2 <= d <= 5, single-pass comparator, rows regenerated instead of parked in HBM (gsweep_impl.cuh)
 cudaError_t launch_gsweep_lo(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 1, 2, 3
 cudaError_t launch_gsweep_hi(const struct SweepArgs& a, int d, cudaStream_t st);   // d = 4, 5

@@ -54,6 +54,7 @@ struct SweepArgs {
     int64_t B; int T;
     int family;
     int force_second_pass;   // test hook (see launch_sweep)
+    int literal;             // gsweep_kernel, d > 1: literal comparator pass for every trajectory (two-pass mode, bit-exact)
     int debug_phase;         // gsweep_kernel timing experiments only (OCO_GSWEEP_DEBUG): 1 = generation only, 2 = play only
     double p_flip;
     const double* tab;       // [groups][T][NF] FTRL scales -(eta0/sqrt(t+1)), padded with -0.0

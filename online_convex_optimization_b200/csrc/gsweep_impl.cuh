@@ -267,7 +267,7 @@ __device__ __forceinline__ void gpath_row_la_a(uint32_t tba, uint32_t k52, GenLA
 // the test hook OCO_SWEEP_FORCE_SECOND_PASS, and by a sequence whose single-pass check failed (never observed).
 // Four rows are requested before the first is consumed (thread-private columns: every warp access is coalesced).
 template <int D>
-static __device__ __noinline__ double gsweep_slab_comp(const double* __restrict__ zr, const uint32_t* __restrict__ lr, int T,
+static __device__ __forceinline__ double gsweep_slab_comp(const double* __restrict__ zr, const uint32_t* __restrict__ lr, int T,
                                                         const double* __restrict__ a_in) {
     double a[D];
 #pragma unroll
@@ -659,19 +659,28 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                     if (a1[0] == 1.0) C = cand[0]; else if (a1[0] == -1.0) C = cand[1];
                     else if (a1[0] == kW) C = cand[2]; else if (a1[0] == -kW) C = cand[3];
                     else if (a1[0] == 0.0) C = (double)T; else found = false;   // not reachable for finite theta
-                    if (found && !p.force_second_pass) { comp = 0.5 * C; reg = cum - comp; return; }
+                    // (theta is finite on g-path data, so one of the five cases holds; a NaN / inf theta gives a NaN comparator
+                    //  and a NaN loss in the reference too.  No literal pass is compiled into the d = 1 kernel: its mere presence
+                    //  after the step loop cost 5 % there -- registers, spills, moves.  The test hook OCO_SWEEP_FORCE_SECOND_PASS
+                    //  is served by the round-1 kernel for d = 1, see launch_sweep.)
+                    comp = found ? 0.5 * C : __longlong_as_double(0x7ff8000000000000LL);
+                    reg = cum - comp;
+                    return;
                 } else if (ok < 0 && !zero_df && !p.force_second_pass && !p.literal) {
                     comp = halfT - nth;
                     reg = (cum - halfT) + nth;
                     return;
                 }
-                {                                               // literal second pass over the slab (exact)
+                if constexpr (D > 1) {                          // literal second pass over the slab (exact)
                     double a[D];
                     ftl_action<D>(th2, a);
-                    // (the slab pointers are recomputed here: keeping zr / lr alive across the step loop costs registers there)
-                    const char* const sR = slab_base + (size_t)((r + 1) & 1) * slab_bytes;
-                    comp = 0.5 * gsweep_slab_comp<D>(reinterpret_cast<const double*>(sR) + tid,
-                                                     reinterpret_cast<const uint32_t*>(sR + row_bytes) + tid, T, a);
+                    // (the slab pointers are recomputed from the kernel arguments: anything kept alive across the step loop
+                    //  for this rare path costs registers -- and moves -- there)
+                    const size_t sb = gsweep_slab_bytes(p.T, D);
+                    const char* const sR = reinterpret_cast<const char*>(p.slab_z) + ((size_t)blockIdx.x * 2 + ((r + 1) & 1)) * sb;
+                    comp = 0.5 * gsweep_slab_comp<D>(reinterpret_cast<const double*>(sR) + threadIdx.x,
+                                                     reinterpret_cast<const uint32_t*>(sR + (size_t)p.T * D * kSweepBlock * sizeof(double)) + threadIdx.x,
+                                                     p.T, a);
                     reg = cum - comp;
                 }
             };

@@ -177,7 +177,8 @@ cudaError_t launch_sweep(int family, uint64_t key_a, uint64_t key_c0, const uint
     a.literal = comparator_mode == 1 ? 0 : 1;
     const char* legacy = getenv("OCO_SWEEP_LEGACY");                             // A/B knob: the round-1 three-phase kernel (d <= 5)
     if (!legacy) legacy = getenv("OCO_SWEEP_D1_LEGACY");
-    const bool use_legacy = legacy && legacy[0] == '1' && d <= 5;
+    // (d = 1 with the test hook: the literal second pass lives in the round-1 kernel only, see gsweep_impl.cuh)
+    const bool use_legacy = (legacy && legacy[0] == '1' && d <= 5) || (d == 1 && a.force_second_pass);
     if (family == FAM_GPATH && !use_legacy) {
         // software-pipelined generate / play kernel (gsweep_impl.cuh), any d <= 8: d = 1 keeps the exact candidate-sum
         // comparator (either mode, bit-exact); d >= 2: OCO_COMPARATOR_LINEAR uses T/2 - ||theta_T|| (no second pass over

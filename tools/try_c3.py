@@ -1,4 +1,4 @@
-"""C3 (d = 1, FTL + 8 FTRL) parity + timing: pipelined gsweep kernel vs the round-1 sweep kernel (OCO_SWEEP_D1_LEGACY=1)."""
+"""C3 (d = 1, FTL + 8 FTRL) parity + timing: pipelined gsweep kernel vs the round-1 sweep kernel (OCO_SWEEP_LEGACY=1)."""
 import math, os, sys
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -20,7 +20,7 @@ if "parity" in sys.argv:
 T = 10000
 for B in [int(a) for a in sys.argv[1:] if a.isdigit()] or [1_000_000]:
     for legacy in ("1", "0"):
-        os.environ["OCO_SWEEP_D1_LEGACY"] = legacy
+        os.environ["OCO_SWEEP_LEGACY"] = legacy
         for _ in range(2):
             reg, st = engine.regret_sweep_device("gpath", B, T, 1, alg, eta, want_regret=False)
         torch.cuda.synchronize()

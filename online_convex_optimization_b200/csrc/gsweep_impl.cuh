@@ -267,7 +267,7 @@ __device__ __forceinline__ void gpath_row_la_a(uint32_t tba, uint32_t k52, GenLA
 // the test hook OCO_SWEEP_FORCE_SECOND_PASS, and by a sequence whose single-pass check failed (never observed).
 // Four rows are requested before the first is consumed (thread-private columns: every warp access is coalesced).
 template <int D>
-static __device__ __forceinline__ double gsweep_slab_comp(const double* __restrict__ zr, const uint32_t* __restrict__ lr, int T,
+static __device__ __noinline__ double gsweep_slab_comp(const double* __restrict__ zr, const uint32_t* __restrict__ lr, int T,
                                                         const double* __restrict__ a_in) {
     double a[D];
 #pragma unroll

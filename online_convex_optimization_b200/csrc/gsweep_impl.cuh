@@ -41,6 +41,7 @@
 //   rounding).
 #pragma once
 #include "sweep_impl.cuh"
+#include <type_traits>
 
 namespace oco {
 
@@ -458,171 +459,181 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
         uint32_t wnext = (doB && T > 0) ? __ldcg(lr) : 0u;
         uint32_t slot = 0, slotn = (kRing - 1) * kSlotBytes;    // byte offsets of the ring slots of row t and of row t + kRing - 1
 
-        for (int t0 = 0; t0 < T; t0 += kTabBlock) {
-            const int tn = min(kTabBlock, T - t0);
-            uint32_t lw = wnext;                                // labels of steps t0 .. t0 + 31 (bit = 1: y = -1)
-            if (doB) {
-                if (t0 + kLabelsPerWord < T) wnext = __ldcg(lr + (int64_t)((t0 >> 5) + 1) * kSweepBlock);
-                if constexpr (kStageTab) {
-                    cp_async_wait<kRing - 2>();                 // this lane's copy of the block's scale rows has landed ...
-                    __syncwarp();                               // ... and so have the other lanes' (all past the previous block)
-                    stage_tab(t0 + kTabBlock, ((t0 / kTabBlock) + 1) & 1);      // joins the commit group of step t0
-                }
-            }
-            uint32_t sca = scta + (kStageTab ? ((t0 / kTabBlock) & 1) * kTabBufBytes : 0u);      // scale row of step t
-
-            for (int i = 0; i < tn; ++i) {
-                const int t = t0 + i;
-                // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
-                if (doA) {
-                    double z[D];
-                    gpath_row_la_a<D>(tba, k52, genA, incA, z);
-#pragma unroll
-                    for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
-                    zw += D * kSweepBlock;
-                }
-                // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
-                if (doB) {
-                    cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
-                    double z[D];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) z[j] = lds_f64_v(ringa + slot + j * (kSweepBlock * 8));
-                    const int yhi = (int)((lw << 31) | 0x3ff00000u);    // y = -1.0 iff the label bit is set
-                    lw >>= 1;
-                    const double y = __hiloint2double(yhi, 0);
-                    double scn[NF];
+        // The step loop exists twice: a generic copy with run-time doA / doB (the first and the last round of a CTA, which
+        // only generate / only play) and a copy for the steady state in which both are compile-time true.  In that copy no
+        // uniform branch separates the generating side from the play side, so the tail of the generator (row clip: a
+        // dependent reciprocal chain that feeds nothing but the slab store; for d > 1 the row norm: sqrt + reciprocal) is in
+        // the same basic block as the head of the play section and is scheduled under its loads and chains.
+        auto run_steps = [&](auto both_tag) {
+            constexpr bool kBoth = decltype(both_tag)::value;
+            const bool runA = kBoth || doA, runB = kBoth || doB;
+            for (int t0 = 0; t0 < T; t0 += kTabBlock) {
+                const int tn = min(kTabBlock, T - t0);
+                uint32_t lw = wnext;                                // labels of steps t0 .. t0 + 31 (bit = 1: y = -1)
+                if (runB) {
+                    if (t0 + kLabelsPerWord < T) wnext = __ldcg(lr + (int64_t)((t0 >> 5) + 1) * kSweepBlock);
                     if constexpr (kStageTab) {
-                        if constexpr (NF == 1) scn[0] = lds_f64_v(sca);
-                        else {
-#pragma unroll
-                            for (int k = 0; k < NF; k += 2) {
-                                const double2 v = lds_v2f64_v(sca + k * 8);
-                                scn[k] = v.x; scn[k + 1] = v.y;
-                            }
-                        }
-                        sca += NF * 8;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < NF; ++k) scn[k] = (NF == 1) ? scn1 : __ldg(tp + (int64_t)t * NF + k);
+                        cp_async_wait<kRing - 2>();                 // this lane's copy of the block's scale rows has landed ...
+                        __syncwarp();                               // ... and so have the other lanes' (all past the previous block)
+                        stage_tab(t0 + kTabBlock, ((t0 / kTabBlock) + 1) & 1);      // joins the commit group of step t0
                     }
-                    if constexpr (D == 1) {
-                        // (d = 1 keeps theta itself in th2*: one shared hz = 0.5*z per step beats halving NF scales)
-                        // |z| <= 1 (clipped row), |x| <= 1 (projected action), y = +-1: q - y has the sign of -y unless it
-                        // is exactly 0 (or NaN), so the gradient step of EVERY variant is gz = -y * 0.5 z or nothing
-                        const double z0 = z[0], hz0 = 0.5 * z0;
-                        const double gz = __hiloint2double(__double2hiint(hz0) ^ (~yhi & 0x80000000), __double2loint(hz0));
-                        const double pw = z0 * kW;                      // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
-                        cand[0] = cand[0] + fabs(z0 - y);
-                        cand[1] = cand[1] + fabs(z0 + y);
-                        cand[2] = cand[2] + fabs(pw - y);
-                        cand[3] = cand[3] + fabs(pw + y);
-                        if constexpr (NFTL > 0) {
-                            // FTL action -(1/sqrt(th*th))*th = -th*|fl(1/th)| (sqrt(fl(th*th)) == |th|), branch-free and in the
-                            // same basic block as the FTRL variants below, so that its 12-deep dependent chain is scheduled
-                            // under them (computed even for items whose FTL columns are not written: do_ftl is only tested
-                            // at the end).  th is 0 or 2^-107 <= |th| <= T/2: every row of the g-path is 0 or a double of
-                            // magnitude >= 2^-54 (ziggurat: integer * wi[idx], clipped to [-1, 1]), hence a multiple of
-                            // 2^-106, and th = sum +-0.5 z.  So th*th neither under- nor overflows and rcp_inrange's range
-                            // holds unless th == 0, where the reference plays 0 (any zero: z*(+-0) - y == -y exactly).
-                            const double rc = rcp_inrange(th2l[0]);
-                            const double x = (th2l[0] == 0.0) ? 0.0 : -fabs(rc) * th2l[0];
-                            const double df = z0 * x - y;
-                            Sl = Sl + fabs(df);
-                            add_if_nonzero(th2l[0], df, gz);                    // zero / NaN diff: no step (fast_algorithms.py:27-34)
-                        }
-                        // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
-                        // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
-                        // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
-                        // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
-#ifndef OCO_GSWEEP_D1_GROUP
-#define OCO_GSWEEP_D1_GROUP 4               // variants handled together (tuning knob: 2 needs fewer temporaries, 4 gives more ILP)
-#endif
-                        constexpr int H = NF >= OCO_GSWEEP_D1_GROUP ? OCO_GSWEEP_D1_GROUP : NF;
-#pragma unroll
-                        for (int h0 = 0; h0 < NF; h0 += H) {
-                            double x1[H], n2v[H];
-                            int top = 0;                                // max over the half of the high word of n2 (n2 >= 0 or NaN)
-#pragma unroll
-                            for (int k = 0; k < H; ++k) {
-                                x1[k] = scn[h0 + k] * th2r[h0 + k][0];
-                                n2v[k] = x1[k] * x1[k];
-                                top = max(top, __double2hiint(n2v[k]));
-                            }
-                            if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
-                                if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
-#pragma unroll
-                                    for (int k = 0; k < H; ++k) {
-                                        double xx[1] = {x1[k]};
-                                        project_unit_ball<1>(xx, n2v[k], mask);
-                                        x1[k] = xx[0];
-                                    }
-                                } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
-#pragma unroll
-                                    for (int k = 0; k < H; ++k) {
-                                        // (select on the FACTOR: the reciprocal chains of all variants stay in this basic block
-                                        //  and interleave; `if (need) x *= fac` let the compiler sink one chain under a branch)
-                                        const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: replaced by 1.0
-                                        x1[k] = x1[k] * ((n2v[k] <= 1.0) ? 1.0 : fac);
-                                    }
+                }
+                uint32_t sca = scta + (kStageTab ? ((t0 / kTabBlock) & 1) * kTabBufBytes : 0u);      // scale row of step t
+
+                for (int i = 0; i < tn; ++i) {
+                    const int t = t0 + i;
+                    // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab
+                    if (runA) {
+                        double z[D];
+                        gpath_row_la_a<D>(tba, k52, genA, incA, z);
+    #pragma unroll
+                        for (int j = 0; j < D; ++j) __stcg(zw + j * kSweepBlock, z[j]);
+                        zw += D * kSweepBlock;
+                    }
+                    // ---- play row t of item r - 1 (fast_algorithms.py:99-111)
+                    if (runB) {
+                        cp_async_wait<kRing - 2>();                     // all but the two youngest groups: row t has landed
+                        double z[D];
+    #pragma unroll
+                        for (int j = 0; j < D; ++j) z[j] = lds_f64_v(ringa + slot + j * (kSweepBlock * 8));
+                        const int yhi = (int)((lw << 31) | 0x3ff00000u);    // y = -1.0 iff the label bit is set
+                        lw >>= 1;
+                        const double y = __hiloint2double(yhi, 0);
+                        double scn[NF];
+                        if constexpr (kStageTab) {
+                            if constexpr (NF == 1) scn[0] = lds_f64_v(sca);
+                            else {
+    #pragma unroll
+                                for (int k = 0; k < NF; k += 2) {
+                                    const double2 v = lds_v2f64_v(sca + k * 8);
+                                    scn[k] = v.x; scn[k + 1] = v.y;
                                 }
                             }
-#pragma unroll
-                            for (int k = 0; k < H; ++k) {
-                                const double df = z0 * x1[k] - y;
-                                Sr[h0 + k] = Sr[h0 + k] + fabs(df);
-                                add_if_nonzero(th2r[h0 + k][0], df, gz);
-                            }
+                            sca += NF * 8;
+                        } else {
+    #pragma unroll
+                            for (int k = 0; k < NF; ++k) scn[k] = (NF == 1) ? scn1 : __ldg(tp + (int64_t)t * NF + k);
                         }
-                    } else {
-                    if (NFTL > 0 && do_ftl) {
-                        // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
-                        double x[D];
-                        ftl_action<D>(th2l, x);
-                        const double df = dot_seq<D>(z, x) - y;
-                        Sl = Sl + fabs(df);
-                        const int dhi = __double2hiint(df);
-                        okl &= dhi ^ yhi;
-                        if (df > 0.0 || df < 0.0) {
-                            const int sgn = dhi & 0x80000000;
-#pragma unroll
-                            for (int j = 0; j < D; ++j)
-                                th2l[j] = th2l[j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
-                        } else zero_df = true;
+                        if constexpr (D == 1) {
+                            // (d = 1 keeps theta itself in th2*: one shared hz = 0.5*z per step beats halving NF scales)
+                            // |z| <= 1 (clipped row), |x| <= 1 (projected action), y = +-1: q - y has the sign of -y unless it
+                            // is exactly 0 (or NaN), so the gradient step of EVERY variant is gz = -y * 0.5 z or nothing
+                            const double z0 = z[0], hz0 = 0.5 * z0;
+                            const double gz = __hiloint2double(__double2hiint(hz0) ^ (~yhi & 0x80000000), __double2loint(hz0));
+                            const double pw = z0 * kW;                      // fl(z*(-w)) = -fl(z*w), fl(-a - y) = -fl(a + y)
+                            cand[0] = cand[0] + fabs(z0 - y);
+                            cand[1] = cand[1] + fabs(z0 + y);
+                            cand[2] = cand[2] + fabs(pw - y);
+                            cand[3] = cand[3] + fabs(pw + y);
+                            if constexpr (NFTL > 0) {
+                                // FTL action -(1/sqrt(th*th))*th = -th*|fl(1/th)| (sqrt(fl(th*th)) == |th|), branch-free and in the
+                                // same basic block as the FTRL variants below, so that its 12-deep dependent chain is scheduled
+                                // under them (computed even for items whose FTL columns are not written: do_ftl is only tested
+                                // at the end).  th is 0 or 2^-107 <= |th| <= T/2: every row of the g-path is 0 or a double of
+                                // magnitude >= 2^-54 (ziggurat: integer * wi[idx], clipped to [-1, 1]), hence a multiple of
+                                // 2^-106, and th = sum +-0.5 z.  So th*th neither under- nor overflows and rcp_inrange's range
+                                // holds unless th == 0, where the reference plays 0 (any zero: z*(+-0) - y == -y exactly).
+                                const double rc = rcp_inrange(th2l[0]);
+                                const double x = (th2l[0] == 0.0) ? 0.0 : -fabs(rc) * th2l[0];
+                                const double df = z0 * x - y;
+                                Sl = Sl + fabs(df);
+                                add_if_nonzero(th2l[0], df, gz);                    // zero / NaN diff: no step (fast_algorithms.py:27-34)
+                            }
+                            // the NF FTRL variants are independent chains (fast_algorithms.py:52-66, 105-111),
+                            // handled HALF by half (variants are usually passed in eta0 order: the small-eta half almost never
+                            // projects, the large-eta half almost always): per half all actions first, one vote, branch-free
+                            // reciprocals the scheduler can interleave, then the steps -- half the temporaries live at a time
+    #ifndef OCO_GSWEEP_D1_GROUP
+    #define OCO_GSWEEP_D1_GROUP 4               // variants handled together (tuning knob: 2 needs fewer temporaries, 4 gives more ILP)
+    #endif
+                            constexpr int H = NF >= OCO_GSWEEP_D1_GROUP ? OCO_GSWEEP_D1_GROUP : NF;
+    #pragma unroll
+                            for (int h0 = 0; h0 < NF; h0 += H) {
+                                double x1[H], n2v[H];
+                                int top = 0;                                // max over the half of the high word of n2 (n2 >= 0 or NaN)
+    #pragma unroll
+                                for (int k = 0; k < H; ++k) {
+                                    x1[k] = scn[h0 + k] * th2r[h0 + k][0];
+                                    n2v[k] = x1[k] * x1[k];
+                                    top = max(top, __double2hiint(n2v[k]));
+                                }
+                                if (__any_sync(mask, top >= 0x3ff00000)) {              // some n2 >= 1.0 in the warp
+                                    if (__any_sync(mask, top >= 0x7c200000)) {          // n2 > ~1e290, inf or NaN: exact slow path
+    #pragma unroll
+                                        for (int k = 0; k < H; ++k) {
+                                            double xx[1] = {x1[k]};
+                                            project_unit_ball<1>(xx, n2v[k], mask);
+                                            x1[k] = xx[0];
+                                        }
+                                    } else {                                            // sqrt(fl(x*x)) == |x|, x * (1/|x|) == x * |1/x|
+    #pragma unroll
+                                        for (int k = 0; k < H; ++k) {
+                                            // (select on the FACTOR: the reciprocal chains of all variants stay in this basic block
+                                            //  and interleave; `if (need) x *= fac` let the compiler sink one chain under a branch)
+                                            const double fac = fabs(rcp_inrange(x1[k]));   // garbage where n2 <= 1: replaced by 1.0
+                                            x1[k] = x1[k] * ((n2v[k] <= 1.0) ? 1.0 : fac);
+                                        }
+                                    }
+                                }
+    #pragma unroll
+                                for (int k = 0; k < H; ++k) {
+                                    const double df = z0 * x1[k] - y;
+                                    Sr[h0 + k] = Sr[h0 + k] + fabs(df);
+                                    add_if_nonzero(th2r[h0 + k][0], df, gz);
+                                }
+                            }
+                        } else {
+                        if (NFTL > 0 && do_ftl) {
+                            // FTL action of theta = 0.5*theta2: n2' = 4 n2, -(1/sqrt(n2')) = 0.5 * -(1/sqrt(n2)): same x bit for bit
+                            double x[D];
+                            ftl_action<D>(th2l, x);
+                            const double df = dot_seq<D>(z, x) - y;
+                            Sl = Sl + fabs(df);
+                            const int dhi = __double2hiint(df);
+                            okl &= dhi ^ yhi;
+                            if (df > 0.0 || df < 0.0) {
+                                const int sgn = dhi & 0x80000000;
+    #pragma unroll
+                                for (int j = 0; j < D; ++j)
+                                    th2l[j] = th2l[j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                            } else zero_df = true;
+                        }
+    #pragma unroll
+                        for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
+                            const double sch = 0.5 * scn[k];             // (0.5*scale) * theta2 == scale * theta
+                            double x[D];
+    #pragma unroll
+                            for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
+                            double n2 = x[0] * x[0];
+    #pragma unroll
+                            for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
+                            project_unit_ball<D>(x, n2, mask);
+                            const double df = dot_seq<D>(z, x) - y;
+                            Sr[k] = Sr[k] + fabs(df);
+                            const int dhi = __double2hiint(df);
+                            okr[k] &= dhi ^ yhi;
+                            if (df > 0.0 || df < 0.0) {
+                                const int sgn = dhi & 0x80000000;
+    #pragma unroll
+                                for (int j = 0; j < D; ++j)
+                                    th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
+                            } else zero_df = true;
+                        }
+                        }
+                        if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
+    #pragma unroll
+                            for (int j = 0; j < D; ++j) cp_async8a(ringa + slotn + j * (kSweepBlock * 8), zrn + j * kSweepBlock);
+                            zrn += D * kSweepBlock;
+                        }
+                        cp_async_commit();
+                        slot = slot + kSlotBytes == kRingBytes ? 0u : slot + kSlotBytes;
+                        slotn = slotn + kSlotBytes == kRingBytes ? 0u : slotn + kSlotBytes;
+                        if constexpr (NF == 1 && !kStageTab) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
                     }
-#pragma unroll
-                    for (int k = 0; k < NF; ++k) {                  // fast_algorithms.py:52-66, 105-111
-                        const double sch = 0.5 * scn[k];             // (0.5*scale) * theta2 == scale * theta
-                        double x[D];
-#pragma unroll
-                        for (int j = 0; j < D; ++j) x[j] = sch * th2r[k][j];
-                        double n2 = x[0] * x[0];
-#pragma unroll
-                        for (int j = 1; j < D; ++j) n2 = n2 + x[j] * x[j];
-                        project_unit_ball<D>(x, n2, mask);
-                        const double df = dot_seq<D>(z, x) - y;
-                        Sr[k] = Sr[k] + fabs(df);
-                        const int dhi = __double2hiint(df);
-                        okr[k] &= dhi ^ yhi;
-                        if (df > 0.0 || df < 0.0) {
-                            const int sgn = dhi & 0x80000000;
-#pragma unroll
-                            for (int j = 0; j < D; ++j)
-                                th2r[k][j] = th2r[k][j] + __hiloint2double(__double2hiint(z[j]) ^ sgn, __double2loint(z[j]));
-                        } else zero_df = true;
-                    }
-                    }
-                    if (t + kRing - 1 < T) {                        // row t + 3 goes into the slot row t - 1 used
-#pragma unroll
-                        for (int j = 0; j < D; ++j) cp_async8a(ringa + slotn + j * (kSweepBlock * 8), zrn + j * kSweepBlock);
-                        zrn += D * kSweepBlock;
-                    }
-                    cp_async_commit();
-                    slot = slot + kSlotBytes == kRingBytes ? 0u : slot + kSlotBytes;
-                    slotn = slotn + kSlotBytes == kRingBytes ? 0u : slotn + kSlotBytes;
-                    if constexpr (NF == 1 && !kStageTab) { if (t + 1 < T) scn1 = __ldg(tp + t + 1); }
                 }
             }
-        }
+        };
+        if (doA && doB) run_steps(std::true_type{}); else run_steps(std::false_type{});
 
         // ---- labels of the generated item: numpy's choice([-1, 1], T) continues the stream after the last normal; one
         // 32-bit draw per label, low half of each raw first (rng_numpy.cuh::LabelCursor), 16 raws per packed word

@@ -12,7 +12,8 @@ head, s1, s2 = s[:h1], s[h1:h2], s[h2:]
 def rebuild(sect, parts):
     lines = sect.split("\n")
     intro_end = next(i for i, l in enumerate(lines) if l.startswith("| metric | value |"))
-    intro = "\n".join(lines[:intro_end])
+    intro = "\n".join(lines[:intro_end]).rstrip("\n") + "\n\n"
     reg_line = next(l for l in lines if l.startswith("Share of issue slots"))
     return (intro + parts[0] + "\n\n" + reg_line + "\n```\n" + parts[1] + "\n```\n\nStall reasons per source line (tools/ncu_stalls.py):\n```\n" + parts[2] + "\n```\n\n")
-open('profiles/r02_ncu_summary.md', 'w').write(head + rebuild(s1, sec["c3"]) + rebuild(s2, sec["c5"]))
+out = head + rebuild(s1, sec["c3"]) + rebuild(s2, sec["c5"])
+open('profiles/r02_ncu_summary.md', 'w').write(out)

@@ -72,6 +72,15 @@ def test_argument_validation_is_value_error():
     assert rc == _lib.OCO_ERR_VALUE and b"d <= 5" in lib.oco_last_error()
     rc = lib.oco_smart_batch(None, None, 1, 0, 4, 3, et, et, 9, None, None, 0, None)
     assert rc == _lib.OCO_ERR_VALUE
+    # shape limits of the round-2 kernels (argument validation comes before any device work)
+    buf = np.zeros(8)
+    dummy = buf.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.oco_smart_batch(dummy, dummy, 1, 1, 4, 257, et, et, 1, dummy, None, 0, None)                    # SMART: d <= 256
+    assert rc == _lib.OCO_ERR_VALUE and b"d <= 256" in lib.oco_last_error()
+    st = (ctypes.c_int * 1)(0)
+    for norm, d_bad, msg in ((2, 17, b"l1 ball: d <= 16"), (1, 33, b"linf ball: d <= 32")):                    # general exact FTL
+        rc = lib.oco_exact_ftl_general_batch(dummy, dummy, 1, 1, 4, d_bad, norm, 50, 1e-8, 0, dummy, None, None, None, st, None)
+        assert rc == _lib.OCO_ERR_VALUE and msg in lib.oco_last_error(), lib.oco_last_error()
 
 
 def test_product_does_not_import_oracle():

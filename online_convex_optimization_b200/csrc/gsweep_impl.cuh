@@ -343,6 +343,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef OCO_GSWEEP_MIN_BLOCKS_NF
 #define OCO_GSWEEP_MIN_BLOCKS_NF 4          // several FTRL variants per thread: more registers, fewer resident CTAs
 #endif
+#ifndef OCO_GSWEEP_UNROLL
+#define OCO_GSWEEP_UNROLL 1                 // tuning knob: unroll factor of the step loop
+#endif
+constexpr int kStepUnroll = OCO_GSWEEP_UNROLL;
 constexpr int kLabelsPerWord = 32;          // packed labels: bit i of word w = 1 iff y[32 w + i] = -1
 constexpr int kTabBlock = 32;               // steps of the FTRL scale table staged at a time (one row per lane)
 static_assert(kTabBlock == kLabelsPerWord && kTabBlock == 32, "the step loop walks blocks of 32: one label word, one scale row per lane");
@@ -480,6 +484,7 @@ __global__ void __launch_bounds__(kSweepBlock, (NF <= 1 ? OCO_GSWEEP_MIN_BLOCKS 
                 }
                 uint32_t sca = scta + (kStageTab ? ((t0 / kTabBlock) & 1) * kTabBufBytes : 0u);      // scale row of step t
 
+#pragma unroll kStepUnroll
                 for (int i = 0; i < tn; ++i) {
                     const int t = t0 + i;
                     // ---- generate row t of item r (fast_algorithms.py:234-236), parked in the slab

@@ -620,7 +620,11 @@ def main():
 
     # ---- e2e through the public host API (host args in, regrets + stats back in host memory)
     e2e_steps = max(1, min(args.steps, 3))
-    engine.regret_sweep("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo, device=local)
+    # warm-up with TWO live results: `out = f()` keeps the previous result alive while the next one is produced, so the
+    # steady state of the loop below uses two output buffers (page-locked, from torch's caching host allocator)
+    w1 = engine.regret_sweep("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo, device=local)
+    w2 = engine.regret_sweep("gpath", B, T, d, wl["alg"], wl["eta"], key_a=0, key_c0=run_lo, device=local)
+    del w1, w2
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -180,6 +181,25 @@ def gen_sequences(family, B: int, T: int, d: int = 5, *, key_a: int = 0, key_c0:
     return z, y
 
 
+_PINNED_MIN_BYTES = 8 << 20
+
+
+def _host_out(shape):
+    """Float64 output array for a host-API call.  Large outputs (>= 8 MB: the per-trajectory regrets of a big sweep) are
+    backed by page-locked memory from torch's caching host allocator when CUDA is available, so the library's
+    device-to-host copy is one DMA at PCIe speed; the driver's staged pageable copy depends on the host (measured 4 to
+    45 ms for 72 MB from box to box).  OCO_PINNED_OUTPUTS=0 keeps plain numpy arrays."""
+    n = int(np.prod(shape))
+    if n * 8 >= _PINNED_MIN_BYTES and os.environ.get("OCO_PINNED_OUTPUTS", "1") != "0":
+        try:
+            torch = _torch()
+            if torch.cuda.is_available():
+                return torch.empty(tuple(int(v) for v in shape), dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.empty(shape)
+
+
 def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int = 0, key_c0: int = 0, keys=None,
                  p_flip: float = -1.0, want_regret: bool = True, full: bool = False, comparator: str = "two_pass",
                  device: int = 0):
@@ -189,9 +209,9 @@ def regret_sweep(family, B: int, T: int, d: int, alg_flags, eta0s, *, key_a: int
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
     af, et = _variants(alg_flags, eta0s)
     A = af.size
-    reg = np.empty((B, A)) if want_regret else None
-    cum = np.empty((B, A)) if full else None
-    comp = np.empty((B, A)) if full else None
+    reg = _host_out((B, A)) if want_regret else None
+    cum = _host_out((B, A)) if full else None
+    comp = _host_out((B, A)) if full else None
     stats = np.zeros((A, 4))
     k = _keys(keys, B)
     _lib.check(_lib.load().oco_regret_sweep_mode_host(fam, key_a, key_c0, _vp(k), B, T, d, float(p_flip), _vp(af), _vp(et), A,
